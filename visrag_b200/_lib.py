@@ -1,0 +1,83 @@
+"""ctypes binding of the C-ABI library ``libvisrag_b200.so`` (include/visrag_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every kernel is launched through the C ABI
+with raw device pointers. There is NO fallback: if the shared library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvisrag_b200.so")
+
+VR_BF16, VR_F16, VR_F32 = 0, 1, 2
+VR_EPI_LINEAR, VR_EPI_ROPE, VR_EPI_SWIGLU = 0, 1, 2
+
+
+class GemmEpilogue(C.Structure):
+    """Mirror of ``vr_gemm_epilogue``."""
+
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("out_dtype", C.c_int32),
+        ("act_gelu", C.c_int32),
+        ("scale", C.c_float),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p),
+        ("rowadd", C.c_void_p),
+        ("rowadd_period", C.c_int32),
+        ("positions", C.c_void_p),
+        ("rope_cos", C.c_void_p),
+        ("rope_sin", C.c_void_p),
+        ("rope_cols", C.c_int32),
+        ("out", C.c_void_p),
+        ("ldo", C.c_int64),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.vr_last_error.restype = C.c_char_p
+    lib.vr_last_error.argtypes = []
+    lib.vr_abi_version.restype = i32
+    lib.vr_abi_version.argtypes = []
+    lib.vr_gemm.restype = i32
+    lib.vr_gemm.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, C.POINTER(GemmEpilogue), vp]
+    lib.vr_gemm_tuned.restype = i32
+    lib.vr_gemm_tuned.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, C.POINTER(GemmEpilogue), i32, vp]
+    _ = f32
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the C-ABI library. Raises if it was not built: no CPU/PyTorch fallback exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C visrag_b200/csrc`). visrag_b200 has no fallback path."
+            )
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"visrag_b200: {lib().vr_last_error().decode()} (status {rc})")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None passes NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,78 @@
+#include "common.h"
+#include "gemm.cuh"
+
+namespace vr {
+
+template <int BN, int MODE, bool OUT_F32, bool GELU, int AB_FMT>
+static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tb;
+    const bool bf16 = AB_FMT == 1;
+    if (int rc = make_tmap_2d(&ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, bf16)) return rc;
+    if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, bf16)) return rc;
+    auto kern = gemm_tcgen05_kernel<BN, MODE, OUT_F32, GELU, AB_FMT>;
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
+    VR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int BN>
+static int dispatch_mode(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s) {
+    const vr_gemm_epilogue& e = g.epi;
+    switch (e.mode) {
+        case VR_EPI_LINEAR:
+            if (e.out_dtype == VR_F32) {
+                VR_REQUIRE(!e.act_gelu, "vr_gemm: GELU epilogue writes bf16 only");
+                return launch_gemm<BN, VR_EPI_LINEAR, true, false, 1>(A, lda, B, ldb, g, s);
+            }
+            VR_REQUIRE(e.out_dtype == VR_BF16, "vr_gemm: out_dtype must be VR_BF16 or VR_F32");
+            if (e.act_gelu) return launch_gemm<BN, VR_EPI_LINEAR, false, true, 1>(A, lda, B, ldb, g, s);
+            return launch_gemm<BN, VR_EPI_LINEAR, false, false, 1>(A, lda, B, ldb, g, s);
+        case VR_EPI_ROPE:
+            VR_REQUIRE(e.positions && e.rope_cos && e.rope_sin, "vr_gemm: ROPE epilogue needs positions/cos/sin");
+            VR_REQUIRE(g.N % 64 == 0 && e.rope_cols % 64 == 0, "vr_gemm: ROPE needs N and rope_cols multiples of 64");
+            return launch_gemm<BN, VR_EPI_ROPE, false, false, 1>(A, lda, B, ldb, g, s);
+        case VR_EPI_SWIGLU:
+            VR_REQUIRE(g.N % 64 == 0, "vr_gemm: SWIGLU needs N multiple of 64");
+            return launch_gemm<BN, VR_EPI_SWIGLU, false, false, 1>(A, lda, B, ldb, g, s);
+        default:
+            set_error("vr_gemm: unknown epilogue mode %d", e.mode);
+            return 2;
+    }
+}
+
+}  // namespace vr
+
+extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_dtype, int32_t M,
+                             int32_t N, int32_t K, const vr_gemm_epilogue* epi, int32_t block_n, void* stream) {
+    using namespace vr;
+    VR_REQUIRE(A && B && epi && epi->out, "vr_gemm: null pointer argument");
+    VR_REQUIRE(M > 0 && N > 0 && K > 0, "vr_gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    VR_REQUIRE(ab_dtype == VR_BF16, "vr_gemm: only bf16 operands are instantiated (got dtype %d)", ab_dtype);
+    VR_REQUIRE(N % 8 == 0, "vr_gemm: N=%d must be a multiple of 8", N);
+    VR_REQUIRE(K % 8 == 0, "vr_gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", K);
+    const int64_t out_cols = epi->mode == VR_EPI_SWIGLU ? N / 2 : N;
+    VR_REQUIRE(epi->ldo >= out_cols && epi->ldo % 8 == 0, "vr_gemm: ldo=%lld too small or not a multiple of 8",
+               (long long)epi->ldo);
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.epi = *epi;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int bn = block_n;
+    if (bn == 0) bn = (N >= 256) ? 256 : 128;
+    if (bn == 256) return dispatch_mode<256>(A, lda, B, ldb, g, s);
+    if (bn == 128) return dispatch_mode<128>(A, lda, B, ldb, g, s);
+    set_error("vr_gemm: block_n must be 0, 128 or 256");
+    return 2;
+}
+
+extern "C" int vr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_dtype, int32_t M, int32_t N,
+                       int32_t K, const vr_gemm_epilogue* epi, void* stream) {
+    return vr_gemm_tuned(A, lda, B, ldb, ab_dtype, M, N, K, epi, 0, stream);
+}
