@@ -68,6 +68,69 @@ typedef struct {
 int vr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_dtype, int32_t M, int32_t N, int32_t K,
             const vr_gemm_epilogue* epi, void* stream);
 
+
+/* ------------------------------------------------------------------------------------
+ * Fused softmax(Q K^T * scale) V on tcgen05 (S and the P.V partial product live in TMEM,
+ * P is re-staged through 128B-swizzled shared memory, running max/sum/O in registers).
+ * Replaces F.scaled_dot_product_attention in timm/models/vision_transformer.py:92-96 (ViT,
+ * 16 heads x 72, no mask), modeling_minicpm.py:895-903 (MiniCPM, causal + right padding ->
+ * here: packed var-len sequences, no padding rows at all) and nn.MultiheadAttention in
+ * resampler.py:159-163 (64 learned queries x N keys, 18 heads x 128).
+ * q/k/v are bf16 row-major token matrices; head h starts at column *_col0 + h*head_stride
+ * (head_stride = head_dim rounded up to a multiple of 16; pad columns must hold zeros).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    const void* q;  int64_t ldq;  int64_t q_rows;   /* q_rows: rows in the q buffer (TMA bound) */
+    const void* k;  int64_t ldk;
+    const void* v;  int64_t ldv;  int64_t kv_rows;  /* rows in the k and v buffers */
+    int32_t q_col0, k_col0, v_col0;
+    int32_t head_stride;      /* 64, 80 or 128 */
+    int32_t head_dim;         /* 64, 72 or 128: output columns per head */
+    int32_t heads, batch;
+    const int32_t* cu_q;      /* [batch+1] packed query offsets, or NULL: every item uses q rows [0, max_q) */
+    const int32_t* cu_k;      /* [batch+1] packed key offsets */
+    int32_t max_q, max_k;     /* longest query / key sequence (grid sizing) */
+    int32_t causal;
+    float scale;
+    void* out; int64_t ldo;   /* bf16; row = cu_q ? cu_q[b]+i : b*max_q+i ; head h at column h*head_dim */
+} vr_attn_params;
+
+int vr_attention(const vr_attn_params* p, void* stream);
+
+
+/* ------------------------------------------------------------------------------------
+ * HBM-bound standalone kernels (128-bit vectorised, one pass over the activation).
+ * ---------------------------------------------------------------------------------- */
+
+/* uint8 HWC slices -> normalised bf16 patch matrix (ToTensor + Normalize(0.5,0.5) + the unfold of the
+ * 14x14/stride-14 patch conv): modeling_minicpmv.py:84-92 + timm/layers/patch_embed.py:87.
+ * pixels: [n_slices, h, w, 3] uint8 (h, w multiples of `patch`); out: [n_slices*(h/patch)*(w/patch), ldo] bf16,
+ * column c*patch*patch + ky*patch + kx (the Conv2d weight's flattening); columns [3*patch^2, ldo) are zeroed. */
+int vr_im2col_norm(const uint8_t* pixels, int32_t n_slices, int32_t h, int32_t w, int32_t patch, void* out, int64_t ldo,
+                   void* stream);
+
+/* LayerNorm over the last dim (timm vision_transformer.py:142,155,525; resampler.py:155,166): fp32 in -> bf16 out.
+ * If out2 != NULL also writes out2 = LN(x) + add[row % add_period] (bf16) — the resampler's K input (kv + pos). */
+int vr_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int32_t rows, int32_t dim,
+                 void* out, int64_t ldo, void* out2, const float* add, int32_t add_period, void* stream);
+
+/* RMSNorm (modeling_minicpm.py:119-123): fp32 in -> bf16 out. */
+int vr_rmsnorm(const float* x, int64_t ldx, const float* gamma, float eps, int32_t rows, int32_t dim, void* out, int64_t ldo,
+               void* stream);
+
+/* LM input assembly (modeling_minicpmv.py:139-166): for packed token t,
+ *   src[t] >= 0 : h[t] = vision[src[t]]            (resampler output row, fp32)
+ *   src[t] <  0 : h[t] = embed[-(src[t]+1)] * scale_emb   (bf16 table)
+ * h: [tokens, dim] fp32. */
+int vr_build_lm_input(const int32_t* src, int32_t tokens, int32_t dim, const void* embed_bf16, float scale_emb,
+                      const float* vision, int64_t ldv, float* h, int64_t ldh, void* stream);
+
+/* Final RMSNorm + pooling + L2 normalise (modeling_minicpm.py:1280; dense_retrieval_model.py:170-223):
+ * per packed sequence b (rows cu[b]..cu[b+1]) of h [tokens, dim] fp32 -> reps [batch, dim] fp32.
+ * pooling: 0 wmean (w_t = t+1), 1 mean, 2 lasttoken, 3 cls. normalise: x / max(||x||, 1e-12). */
+int vr_pool_norm(const float* h, int64_t ldh, const float* gamma, float eps, const int32_t* cu, int32_t batch, int32_t dim,
+                 int32_t pooling, int32_t normalize, float* reps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,8 +103,8 @@ def build_reference_model(cfg, state_dict: Dict[str, "torch.Tensor"], attn_imple
         raise RuntimeError(f"state_dict mismatch: missing={missing[:8]} unexpected={unexpected[:8]}")
     lm.load_state_dict({k: v.float() for k, v in state_dict.items()}, strict=False)
     margs = R["ModelArguments"](model_name_or_path="synthetic", pooling=pooling, normalize=True)
-    model = R["DRModelForInference"](lm_q=lm, lm_p=lm, tied=True, feature="last_hidden_state", pooling=pooling,
-                                     normalize=True, model_args=margs)
+    model = R["DRModelForInference"](lm_q=lm, feature="last_hidden_state", pooling=pooling, normalize=True,
+                                     model_args=margs)
     return model
 
 

@@ -1,0 +1,230 @@
+"""GPU bring-up check of the encode path, stage by stage (run on the B200 box through gpurun).
+Each stage runs in its own subprocess; results -> stdout and gpurun_out/check_encode.log."""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def report(name, got, want, tol):
+    import torch
+
+    got, want = got.float().cpu(), want.float().cpu()
+    err = (got - want).abs().max().item()
+    ref = want.abs().max().item()
+    bad = not (err <= tol * max(ref, 1e-3)) or not torch.isfinite(got).all().item()
+    print(f"{'FAIL' if bad else 'ok  '} {name}: max_abs_err={err:.4e} ref_max={ref:.3e}", flush=True)
+    return not bad
+
+
+def stage_elementwise():
+    import torch
+    import torch.nn.functional as F
+    from visrag_b200 import ops
+
+    torch.manual_seed(0)
+    ok = True
+    dev = "cuda"
+    px = torch.randint(0, 256, (3, 28, 42, 3), dtype=torch.uint8, device=dev)
+    got = ops.im2col_norm(px, 14, 640)
+    x = ((px.float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2)  # [S,3,h,w]
+    want = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    ok &= report("im2col", got[:, :588], want.bfloat16(), 1e-6)
+    ok &= report("im2col pad", got[:, 588:], torch.zeros_like(got[:, 588:]), 1e-6)
+    for D in (288, 1152, 2304):
+        x = torch.randn(1000, D, device=dev) * 3 + 1
+        g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+        add = torch.randn(37, D, device=dev)
+        o1, o2 = ops.layernorm(x, g, b, 1e-6, add=add)
+        ref = F.layer_norm(x, (D,), g, b, 1e-6)
+        ok &= report(f"layernorm D={D}", o1, ref, 1e-2)
+        ok &= report(f"layernorm+add D={D}", o2, ref + add[torch.arange(1000, device=dev) % 37], 1e-2)
+        o = ops.rmsnorm(x, g, 1e-5)
+        ok &= report(f"rmsnorm D={D}", o, x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * g, 1e-2)
+    D = 256
+    emb = torch.randn(512, D, device=dev).bfloat16()
+    vis = torch.randn(128, D, device=dev)
+    src = torch.tensor([-1 - 5, 0, 1, 127, -1 - 511, -1 - 0], dtype=torch.int32, device=dev)
+    h = ops.build_lm_input(src, emb, 12.0, vis)
+    want = torch.stack([emb[5].float() * 12, vis[0], vis[1], vis[127], emb[511].float() * 12, emb[0].float() * 12])
+    ok &= report("build_lm_input", h, want, 1e-6)
+    # pool
+    lens = [1, 5, 68, 300]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    hh = torch.randn(sum(lens), 2304, device=dev)
+    g = torch.randn(2304, device=dev)
+    for mode in ("wmean", "mean", "lasttoken", "cls"):
+        got = ops.pool_norm(hh, g, 1e-5, cu, mode, True)
+        outs = []
+        for i, n in enumerate(lens):
+            x = hh[cu[i]:cu[i + 1]]
+            x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * g
+            if mode == "wmean":
+                w = torch.arange(1, n + 1, device=dev).float()
+                r = (x * w[:, None]).sum(0) / w.sum()
+            elif mode == "mean":
+                r = x.mean(0)
+            elif mode == "lasttoken":
+                r = x[-1]
+            else:
+                r = x[0]
+            outs.append(F.normalize(r[None], dim=1)[0])
+        ok &= report(f"pool_norm {mode}", got, torch.stack(outs), 1e-5)
+    return ok
+
+
+def _attn_ref(q, k, v, scale, causal):
+    import torch
+
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    if causal:
+        Lq, Lk = s.shape[-2], s.shape[-1]
+        m = torch.ones(Lq, Lk, dtype=torch.bool, device=s.device).tril(Lk - Lq)
+        s = s.masked_fill(~m, float("-inf"))
+    return torch.softmax(s, -1) @ v.float()
+
+
+def stage_attention():
+    import torch
+    from visrag_b200 import ops
+
+    torch.manual_seed(1)
+    ok = True
+    dev = "cuda"
+    # --- ViT style: heads x 72 padded to 80, non-causal, fixed N per slice
+    for (S, N, nh) in [(1, 128, 1), (1, 256, 2), (3, 1024, 4), (2, 1036, 16), (5, 130, 3)]:
+        hd, hs = 72, 80
+        qkv = torch.zeros(S * N, 3, nh, hs, device=dev)
+        qkv[..., :hd] = torch.randn(S * N, 3, nh, hd, device=dev)
+        qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
+        cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=dev)
+        out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device=dev)
+        ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
+                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out)
+        torch.cuda.synchronize()
+        x = qkv.view(S, N, 3, nh, hs)[..., :hd].permute(2, 0, 3, 1, 4)  # [3,S,nh,N,hd]
+        want = _attn_ref(x[0], x[1], x[2], hd ** -0.5, False).permute(0, 2, 1, 3).reshape(S * N, nh * hd)
+        ok &= report(f"attn vit S={S} N={N} heads={nh}", out, want, 2e-2)
+    # --- LM style: causal var-len, hd 64
+    for lens in ([68], [1, 5, 68, 127, 128, 129, 300], [670, 33]):
+        nh, hd = 4, 64
+        H = nh * hd
+        T = sum(lens)
+        qkv = torch.randn(T, 3 * H, device=dev).bfloat16()
+        cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+        out = torch.zeros(T, H, dtype=torch.bfloat16, device=dev)
+        ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=H, v_col0=2 * H, head_stride=64, head_dim=64, heads=nh, batch=len(lens),
+                      cu_k=cu, max_k=max(lens), cu_q=cu, max_q=max(lens), causal=True, scale=hd ** -0.5, out=out)
+        torch.cuda.synchronize()
+        wants = []
+        for i, n in enumerate(lens):
+            x = qkv[cu[i]:cu[i + 1]].view(n, 3, nh, hd).permute(1, 2, 0, 3)
+            wants.append(_attn_ref(x[0], x[1], x[2], hd ** -0.5, True).permute(1, 0, 2).reshape(n, H))
+        ok &= report(f"attn lm causal lens={lens}", out, torch.cat(wants), 2e-2)
+    # --- resampler style: 64 shared queries, hd 128
+    for (S, N, nh) in [(1, 1024, 2), (3, 1036, 18), (2, 100, 2)]:
+        E = nh * 128
+        q = torch.zeros(128, E, device=dev)
+        q[:64] = torch.randn(64, E, device=dev)
+        q = q.bfloat16()
+        k = torch.randn(S * N, E, device=dev).bfloat16()
+        v = torch.randn(S * N, E, device=dev).bfloat16()
+        cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=dev)
+        out = torch.zeros(S * 64, E, dtype=torch.bfloat16, device=dev)
+        ops.attention(q, k, v, q_col0=0, k_col0=0, v_col0=0, head_stride=128, head_dim=128, heads=nh, batch=S, cu_k=cu,
+                      max_k=N, cu_q=None, max_q=64, causal=False, scale=128 ** -0.5, out=out)
+        torch.cuda.synchronize()
+        Q = q[:64].view(64, nh, 128).permute(1, 0, 2)[None]
+        K = k.view(S, N, nh, 128).permute(0, 2, 1, 3)
+        V = v.view(S, N, nh, 128).permute(0, 2, 1, 3)
+        want = _attn_ref(Q, K, V, 128 ** -0.5, False).permute(0, 2, 1, 3).reshape(S * 64, E)
+        ok &= report(f"attn resampler S={S} N={N} heads={nh}", out, want, 2e-2)
+    return ok
+
+
+def _tiny():
+    from tests.helpers import load_case
+    from visrag_b200.weights import random_state_dict
+
+    cfg, wseed, pages, queries, z = load_case("tiny_v1")
+    return cfg, random_state_dict(cfg, wseed), pages, queries, z
+
+
+def stage_vision():
+    import numpy as np
+    import torch
+    from oracle import restated as O
+    from visrag_b200 import host
+    from visrag_b200.encoder import VisRAGEngine
+
+    cfg, sd, pages, queries, z = _tiny()
+    eng = VisRAGEngine(cfg, sd)
+    ok = True
+    for img in (pages[0], pages[3]):
+        sl = host.render_slices(img, host.plan_slices(*img.size, cfg))
+        for s in sl[:2]:
+            px = torch.from_numpy(s)[None].cuda()
+            tok = eng.vit_tokens(px)
+            from PIL import Image
+
+            pil = Image.fromarray(s)
+            want = O.vit_forward(sd, cfg, O.pixel_values(pil))
+            ok &= report(f"vit tokens {s.shape}", tok, want, 3e-2)
+            gh, gw = s.shape[0] // 14, s.shape[1] // 14
+            out = torch.empty(64, cfg.hidden, device="cuda")
+            eng.resample(tok, 1, gh, gw, out)
+            want_r = O.resampler_forward(sd, cfg, want, gh, gw)
+            ok &= report(f"resampler {s.shape}", out, want_r, 3e-2)
+    return ok
+
+
+def stage_encode():
+    import numpy as np
+    import torch
+    from oracle import restated as O
+    from tests.helpers import cosine_rows
+    from visrag_b200.encoder import VisRAGEngine
+    from visrag_b200.tokenizer_stub import StubTokenizer
+
+    cfg, sd, pages, queries, z = _tiny()
+    eng = VisRAGEngine(cfg, sd)
+    tok = StubTokenizer(cfg.vocab)
+    p = eng.encode([""] * len(pages), pages, tok).cpu().numpy()
+    q = eng.encode(queries, [None] * len(queries), tok).cpu().numpy()
+    ok = True
+    cp, cq = cosine_rows(p, z["page_reps"]), cosine_rows(q, z["query_reps"])
+    print("page cosine vs reference golden:", np.round(cp, 5), flush=True)
+    print("query cosine vs reference golden:", np.round(cq, 5), flush=True)
+    ok &= bool((cp > 0.999).all() and (cq > 0.999).all())
+    S = q @ p.T
+    top = np.argsort(-S, axis=1)[:, : z["topk_indices"].shape[1]]
+    print("topk ours\n", top, "\nreference\n", z["topk_indices"], flush=True)
+    ok &= bool((np.sort(top, 1) == np.sort(z["topk_indices"], 1)).all())
+    # mixed batch in one call == separate calls
+    both = eng.encode([""] * 2 + queries[:2], pages[:2] + [None, None], tok).cpu().numpy()
+    ok &= report("mixed batch pages", torch.from_numpy(both[:2]), torch.from_numpy(p[:2]), 2e-2)
+    ok &= report("mixed batch queries", torch.from_numpy(both[2:]), torch.from_numpy(q[:2]), 2e-2)
+    print("norms", np.linalg.norm(p, axis=1), flush=True)
+    return ok
+
+
+STAGES = {"elementwise": stage_elementwise, "attention": stage_attention, "vision": stage_vision, "encode": stage_encode}
+
+if __name__ == "__main__":
+    if len(sys.argv) == 2:
+        sys.exit(0 if STAGES[sys.argv[1]]() else 1)
+    os.makedirs("gpurun_out", exist_ok=True)
+    log = open("gpurun_out/check_encode.log", "w")
+    rc_all = 0
+    for st in STAGES:
+        t0 = time.time()
+        p = subprocess.run([sys.executable, __file__, st], capture_output=True, text=True, timeout=900, cwd=ROOT)
+        msg = f"=== {st} rc={p.returncode} ({time.time()-t0:.1f}s)\n{p.stdout}{p.stderr[-4000:]}\n"
+        print(msg, flush=True)
+        log.write(msg)
+        log.flush()
+        rc_all |= p.returncode
+    sys.exit(rc_all)

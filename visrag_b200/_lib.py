@@ -37,6 +37,23 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+class AttnParams(C.Structure):
+    """Mirror of ``vr_attn_params``."""
+
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64), ("q_rows", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64), ("kv_rows", C.c_int64),
+        ("q_col0", C.c_int32), ("k_col0", C.c_int32), ("v_col0", C.c_int32),
+        ("head_stride", C.c_int32), ("head_dim", C.c_int32),
+        ("heads", C.c_int32), ("batch", C.c_int32),
+        ("cu_q", C.c_void_p), ("cu_k", C.c_void_p),
+        ("max_q", C.c_int32), ("max_k", C.c_int32),
+        ("causal", C.c_int32), ("scale", C.c_float),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -50,7 +67,18 @@ def _declare(lib: C.CDLL) -> None:
     lib.vr_gemm.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, C.POINTER(GemmEpilogue), vp]
     lib.vr_gemm_tuned.restype = i32
     lib.vr_gemm_tuned.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, C.POINTER(GemmEpilogue), i32, vp]
-    _ = f32
+    lib.vr_attention.restype = i32
+    lib.vr_attention.argtypes = [C.POINTER(AttnParams), vp]
+    lib.vr_im2col_norm.restype = i32
+    lib.vr_im2col_norm.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp]
+    lib.vr_layernorm.restype = i32
+    lib.vr_layernorm.argtypes = [vp, i64, vp, vp, f32, i32, i32, vp, i64, vp, vp, i32, vp]
+    lib.vr_rmsnorm.restype = i32
+    lib.vr_rmsnorm.argtypes = [vp, i64, vp, f32, i32, i32, vp, i64, vp]
+    lib.vr_build_lm_input.restype = i32
+    lib.vr_build_lm_input.argtypes = [vp, i32, i32, vp, f32, vp, i64, vp, i64, vp]
+    lib.vr_pool_norm.restype = i32
+    lib.vr_pool_norm.argtypes = [vp, i64, vp, f32, vp, i32, i32, i32, i32, vp, vp]
 
 
 def lib() -> C.CDLL:

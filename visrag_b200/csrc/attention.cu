@@ -1,0 +1,59 @@
+#include <string.h>
+#include "common.h"
+#include "attention.cuh"
+
+namespace vr {
+
+template <int HS, bool CAUSAL>
+static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
+    using Cfg = AttCfg<HS>;
+    AttMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    // TMA extents: all columns of the token matrices, rows = buffer rows (out-of-range rows read as zero)
+    const uint64_t qcols = p.ldq, kcols = p.ldk, vcols = p.ldv;
+    if (int rc = make_tmap_2d(&maps.q64, p.q, p.q_rows, qcols, p.ldq, ATT_BM, 64, 128, true)) return rc;
+    if (int rc = make_tmap_2d(&maps.k64, p.k, p.kv_rows, kcols, p.ldk, ATT_BN, 64, 128, true)) return rc;
+    if (int rc = make_tmap_2d(&maps.v64, p.v, p.kv_rows, vcols, p.ldv, ATT_BN, 64, 128, true)) return rc;
+    if (Cfg::HAS16) {
+        if (int rc = make_tmap_2d(&maps.q16, p.q, p.q_rows, qcols, p.ldq, ATT_BM, 16, 32, true)) return rc;
+        if (int rc = make_tmap_2d(&maps.k16, p.k, p.kv_rows, kcols, p.ldk, ATT_BN, 16, 32, true)) return rc;
+        if (int rc = make_tmap_2d(&maps.v16, p.v, p.kv_rows, vcols, p.ldv, ATT_BN, 16, 32, true)) return rc;
+    }
+    AttArgs a;
+    a.q_col0 = p.q_col0; a.k_col0 = p.k_col0; a.v_col0 = p.v_col0;
+    a.head_dim = p.head_dim; a.heads = p.heads; a.batch = p.batch;
+    a.cu_q = p.cu_q; a.cu_k = p.cu_k; a.max_q = p.max_q; a.causal = p.causal;
+    a.scale_log2 = p.scale * 1.4426950408889634f;
+    a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    a.ldo = p.ldo;
+    auto kern = attention_tcgen05_kernel<HS, CAUSAL>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid((p.max_q + ATT_BM - 1) / ATT_BM, p.heads, p.batch);
+    kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a);
+    VR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vr
+
+extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
+    using namespace vr;
+    VR_REQUIRE(p && p->q && p->k && p->v && p->out && p->cu_k, "vr_attention: null pointer argument");
+    VR_REQUIRE(p->heads > 0 && p->batch > 0 && p->max_q > 0 && p->max_k > 0, "vr_attention: empty problem");
+    VR_REQUIRE(p->batch <= 65535 && p->heads <= 65535, "vr_attention: batch/heads exceed grid limits");
+    VR_REQUIRE(p->head_dim <= p->head_stride && p->head_dim % 8 == 0, "vr_attention: head_dim %d vs stride %d",
+               p->head_dim, p->head_stride);
+    VR_REQUIRE(p->ldo % 8 == 0, "vr_attention: ldo must be a multiple of 8");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const bool c = p->causal != 0;
+    switch (p->head_stride) {
+        case 64: return c ? launch_attention<64, true>(*p, s) : launch_attention<64, false>(*p, s);
+        case 80: return c ? launch_attention<80, true>(*p, s) : launch_attention<80, false>(*p, s);
+        case 128: return c ? launch_attention<128, true>(*p, s) : launch_attention<128, false>(*p, s);
+        default: set_error("vr_attention: head_stride must be 64, 80 or 128 (got %d)", p->head_stride); return 2;
+    }
+}

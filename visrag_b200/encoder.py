@@ -1,0 +1,247 @@
+"""B200 engine for the VisRAG-Ret encode path: uint8 slices + packed tokens -> pooled fp32 embeddings.
+
+Replaces the GPU work of `VisRAG_Ret.forward` (`modeling_visrag_ret.py:86-126`), `get_vllm_embedding`
+(`modeling_minicpmv.py:124-171`), the timm ViT, the Resampler and `MiniCPMModel.forward`, plus the pooling of
+`DRModel.encode` (`dense_retrieval_model.py:170-223`). Differences in *schedule* (never in math):
+  * the ViT runs over ALL slices of a batch that share a geometry at once (the reference loops page by page
+    with batch 1, `modeling_minicpmv.py:130-135`);
+  * LM sequences are packed (cu_seqlens) instead of right-padded;
+  * the residual streams stay fp32 in HBM; every GEMM reads bf16 operands and accumulates in fp32 (TMEM).
+Every kernel is a C-ABI call (visrag_b200/ops.py); torch only owns the buffers.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .config import VisRAGConfig
+from .host import PreparedBatch, prepare_batch
+from .weights import sincos_2d
+
+VIT_HEAD_STRIDE = 80  # 72 padded to a multiple of 16 (UMMA K granularity); pad rows of Wqkv are zero
+
+
+def _bf16(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.to(device=dev, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+class VisRAGEngine:
+    """Holds device weights in kernel-ready layouts and runs the encode pipeline."""
+
+    def __init__(self, cfg: VisRAGConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
+                 max_vit_tokens: int = 131072):
+        cfg.validate()
+        L.lib()  # fail loudly if the CUDA library is missing
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.max_vit_tokens = max_vit_tokens
+        sd, dev = state_dict, self.device
+        D, E, H, I = cfg.vit_dim, cfg.hidden, cfg.hidden, cfg.inter
+        nh, hd, hs = cfg.vit_heads, cfg.vit_head_dim, VIT_HEAD_STRIDE
+        with torch.no_grad():
+            # ---- ViT
+            P2 = 3 * cfg.patch_size ** 2
+            self.patch_k = ((P2 + 63) // 64) * 64  # 588 -> 640: TMA rows must be 16-byte multiples
+            w = torch.zeros((D, self.patch_k), dtype=torch.float32)
+            w[:, :P2] = sd["vpm.patch_embed.proj.weight"].float().reshape(D, P2).cpu()
+            self.patch_w = _bf16(w, dev)
+            self.patch_b = _f32(sd["vpm.patch_embed.proj.bias"], dev)
+            self.pos_embed = sd["vpm.pos_embed"].float().cpu()
+            self._pos_cache: Dict[Tuple[int, int], torch.Tensor] = {}
+            self._sincos_cache: Dict[Tuple[int, int], torch.Tensor] = {}
+            self.blocks = []
+            for i in range(cfg.vit_depth):
+                p = f"vpm.blocks.{i}."
+                wq = sd[p + "attn.qkv.weight"].float().cpu().reshape(3, nh, hd, D)
+                bq = sd[p + "attn.qkv.bias"].float().cpu().reshape(3, nh, hd)
+                wpad = torch.zeros((3, nh, hs, D))
+                bpad = torch.zeros((3, nh, hs))
+                wpad[:, :, :hd] = wq
+                bpad[:, :, :hd] = bq
+                self.blocks.append(dict(
+                    n1w=_f32(sd[p + "norm1.weight"], dev), n1b=_f32(sd[p + "norm1.bias"], dev),
+                    qkv_w=_bf16(wpad.reshape(3 * nh * hs, D), dev), qkv_b=_f32(bpad.reshape(-1), dev),
+                    proj_w=_bf16(sd[p + "attn.proj.weight"], dev), proj_b=_f32(sd[p + "attn.proj.bias"], dev),
+                    n2w=_f32(sd[p + "norm2.weight"], dev), n2b=_f32(sd[p + "norm2.bias"], dev),
+                    fc1_w=_bf16(sd[p + "mlp.fc1.weight"], dev), fc1_b=_f32(sd[p + "mlp.fc1.bias"], dev),
+                    fc2_w=_bf16(sd[p + "mlp.fc2.weight"], dev), fc2_b=_f32(sd[p + "mlp.fc2.bias"], dev),
+                ))
+            self.vnorm_w, self.vnorm_b = _f32(sd["vpm.norm.weight"], dev), _f32(sd["vpm.norm.bias"], dev)
+            # ---- Resampler
+            self.rs_kv_w = _bf16(sd["resampler.kv_proj.weight"], dev)
+            self.rs_lnkv = (_f32(sd["resampler.ln_kv.weight"], dev), _f32(sd["resampler.ln_kv.bias"], dev))
+            self.rs_lnpost = (_f32(sd["resampler.ln_post.weight"], dev), _f32(sd["resampler.ln_post.bias"], dev))
+            Win, bin_ = sd["resampler.attn.in_proj_weight"].float(), sd["resampler.attn.in_proj_bias"].float()
+            self.rs_wk, self.rs_bk = _bf16(Win[E:2 * E], dev), _f32(bin_[E:2 * E], dev)
+            self.rs_wv, self.rs_bv = _bf16(Win[2 * E:], dev), _f32(bin_[2 * E:], dev)
+            self.rs_wo, self.rs_bo = _bf16(sd["resampler.attn.out_proj.weight"], dev), _f32(sd["resampler.attn.out_proj.bias"], dev)
+            self.rs_projT = _bf16(sd["resampler.proj"].float().t(), dev)  # y = x @ proj  ->  B operand = proj^T
+            # the query side is input independent (`resampler.py:158-160`): Q = Wq (LN_q(query) + pos_8x8) + bq, once
+            q_in = ops.layernorm(_f32(sd["resampler.query"], dev), _f32(sd["resampler.ln_q.weight"], dev),
+                                 _f32(sd["resampler.ln_q.bias"], dev), 1e-6, add=_f32(sd["resampler.pos_embed"], dev))[1]
+            self.rs_q = torch.zeros((128, E), dtype=torch.bfloat16, device=dev)  # padded to one 128-row query tile
+            ops.gemm(q_in, _bf16(Win[:E], dev), bias=_f32(bin_[:E], dev), out=self.rs_q[: cfg.query_num])
+            # ---- MiniCPM
+            self.embed = _bf16(sd["llm.model.embed_tokens.weight"], dev)
+            self.layers = []
+            for i in range(cfg.layers):
+                p = f"llm.model.layers.{i}."
+                wqkv = torch.cat([sd[p + f"self_attn.{n}_proj.weight"].float() for n in ("q", "k", "v")], dim=0)
+                wg, wu = sd[p + "mlp.gate_proj.weight"].float(), sd[p + "mlp.up_proj.weight"].float()
+                # rows interleaved in blocks of 32 so that gate_j and up_j land in the same epilogue thread
+                wgu = torch.stack([wg.reshape(I // 32, 32, H), wu.reshape(I // 32, 32, H)], dim=1).reshape(2 * I, H)
+                self.layers.append(dict(
+                    in_w=_f32(sd[p + "input_layernorm.weight"], dev), post_w=_f32(sd[p + "post_attention_layernorm.weight"], dev),
+                    qkv_w=_bf16(wqkv, dev), o_w=_bf16(sd[p + "self_attn.o_proj.weight"], dev),
+                    gu_w=_bf16(wgu, dev), down_w=_bf16(sd[p + "mlp.down_proj.weight"], dev),
+                ))
+            self.final_w = _f32(sd["llm.model.norm.weight"], dev)
+            inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2).float() / cfg.head_dim))
+            fr = torch.outer(torch.arange(cfg.max_pos).float(), inv)  # `modeling_minicpm.py:142-182`
+            self.rope_cos, self.rope_sin = _f32(fr.cos(), dev), _f32(fr.sin(), dev)
+            torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------------------------------ tables
+    def _pos_table(self, gh: int, gw: int) -> torch.Tensor:
+        """ViT position embedding resampled to (gh, gw): bicubic + antialias in fp32, once per distinct grid
+        (`timm/layers/pos_embed.py:17-57`; the reference redoes it every forward)."""
+        key = (gh, gw)
+        if key not in self._pos_cache:
+            S, D = self.cfg.vit_pos_grid, self.cfg.vit_dim
+            if gh == S and gw == S:
+                t = self.pos_embed[0]
+            else:
+                p = self.pos_embed.reshape(1, S, S, D).permute(0, 3, 1, 2)
+                p = torch.nn.functional.interpolate(p, size=(gh, gw), mode="bicubic", antialias=True)
+                t = p.permute(0, 2, 3, 1).reshape(gh * gw, D)
+            self._pos_cache[key] = _f32(t, self.device)
+        return self._pos_cache[key]
+
+    def _sincos_table(self, gh: int, gw: int) -> torch.Tensor:
+        key = (gh, gw)
+        if key not in self._sincos_cache:
+            self._sincos_cache[key] = _f32(torch.from_numpy(sincos_2d(self.cfg.hidden, gh, gw)), self.device)
+        return self._sincos_cache[key]
+
+    # ------------------------------------------------------------------------------------------ vision
+    def vit_tokens(self, pixels: torch.Tensor) -> torch.Tensor:
+        """uint8 [S,h,w,3] (device) -> final-LayerNorm ViT tokens bf16 [S*N, D]."""
+        cfg = self.cfg
+        S, h, w, _ = pixels.shape
+        gh, gw = h // cfg.patch_size, w // cfg.patch_size
+        N, D, nh = gh * gw, cfg.vit_dim, cfg.vit_heads
+        M = S * N
+        a = ops.im2col_norm(pixels, cfg.patch_size, self.patch_k)
+        x = ops.gemm(a, self.patch_w, bias=self.patch_b, rowadd=self._pos_table(gh, gw), out_dtype=torch.float32)
+        cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=self.device)
+        qkv = torch.empty((M, 3 * nh * VIT_HEAD_STRIDE), dtype=torch.bfloat16, device=self.device)
+        att = torch.empty((M, D), dtype=torch.bfloat16, device=self.device)
+        scale = cfg.vit_head_dim ** -0.5
+        for blk in self.blocks:
+            y = ops.layernorm(x, blk["n1w"], blk["n1b"], cfg.ln_eps)
+            ops.gemm(y, blk["qkv_w"], bias=blk["qkv_b"], out=qkv)
+            ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * VIT_HEAD_STRIDE, v_col0=2 * nh * VIT_HEAD_STRIDE,
+                          head_stride=VIT_HEAD_STRIDE, head_dim=cfg.vit_head_dim, heads=nh, batch=S, cu_k=cu, max_k=N,
+                          cu_q=cu, max_q=N, causal=False, scale=scale, out=att)
+            ops.gemm(att, blk["proj_w"], bias=blk["proj_b"], resid=x, out=x, out_dtype=torch.float32)
+            y = ops.layernorm(x, blk["n2w"], blk["n2b"], cfg.ln_eps)
+            y = ops.gemm(y, blk["fc1_w"], bias=blk["fc1_b"], gelu=True)
+            ops.gemm(y, blk["fc2_w"], bias=blk["fc2_b"], resid=x, out=x, out_dtype=torch.float32)
+        return ops.layernorm(x, self.vnorm_w, self.vnorm_b, cfg.ln_eps)
+
+    def resample(self, tokens: torch.Tensor, S: int, gh: int, gw: int, out: torch.Tensor) -> None:
+        """ViT tokens bf16 [S*N, D] -> 64 query tokens per slice, written to fp32 `out` [S*64, E]."""
+        cfg = self.cfg
+        E, N, nh = cfg.hidden, gh * gw, cfg.rs_heads
+        kv = ops.gemm(tokens, self.rs_kv_w, out_dtype=torch.float32)
+        v_in, k_in = ops.layernorm(kv, self.rs_lnkv[0], self.rs_lnkv[1], 1e-6, add=self._sincos_table(gh, gw))
+        k = ops.gemm(k_in, self.rs_wk, bias=self.rs_bk)
+        v = ops.gemm(v_in, self.rs_wv, bias=self.rs_bv)
+        cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=self.device)
+        att = torch.empty((S * cfg.query_num, E), dtype=torch.bfloat16, device=self.device)
+        ops.attention(self.rs_q, k, v, q_col0=0, k_col0=0, v_col0=0, head_stride=128, head_dim=128, heads=nh, batch=S,
+                      cu_k=cu, max_k=N, cu_q=None, max_q=cfg.query_num, causal=False, scale=128 ** -0.5, out=att)
+        o = ops.gemm(att, self.rs_wo, bias=self.rs_bo, out_dtype=torch.float32)
+        o = ops.layernorm(o, self.rs_lnpost[0], self.rs_lnpost[1], 1e-6)
+        ops.gemm(o, self.rs_projT, out=out, out_dtype=torch.float32)
+
+    def encode_vision(self, groups: Dict[Tuple[int, int], torch.Tensor], group_row0: Dict[Tuple[int, int], int],
+                      n_slices: int) -> Optional[torch.Tensor]:
+        """All slices of a batch -> fp32 [n_slices*64, E] (slice i occupies rows 64i..64i+63)."""
+        if n_slices == 0:
+            return None
+        cfg = self.cfg
+        out = torch.empty((n_slices * cfg.query_num, cfg.hidden), dtype=torch.float32, device=self.device)
+        for (h, w), px in groups.items():
+            gh, gw = h // cfg.patch_size, w // cfg.patch_size
+            per = max(1, self.max_vit_tokens // (gh * gw))
+            for s0 in range(0, px.shape[0], per):
+                chunk = px[s0:s0 + per]
+                S = chunk.shape[0]
+                r0 = (group_row0[(h, w)] + s0) * cfg.query_num
+                self.resample(self.vit_tokens(chunk), S, gh, gw, out[r0:r0 + S * cfg.query_num])
+        return out
+
+    # ------------------------------------------------------------------------------------------ LM
+    def lm_hidden(self, token_src: torch.Tensor, positions: torch.Tensor, cu: torch.Tensor, max_len: int,
+                  vision: Optional[torch.Tensor]) -> torch.Tensor:
+        """Packed decoder: returns the fp32 residual stream BEFORE the final RMSNorm, [T, H]."""
+        cfg = self.cfg
+        H, nh = cfg.hidden, cfg.heads
+        B = cu.shape[0] - 1
+        h = ops.build_lm_input(token_src, self.embed, cfg.scale_emb, vision)
+        T = h.shape[0]
+        qkv = torch.empty((T, 3 * H), dtype=torch.bfloat16, device=self.device)
+        att = torch.empty((T, H), dtype=torch.bfloat16, device=self.device)
+        s = cfg.depth_scale
+        for lyr in self.layers:
+            a = ops.rmsnorm(h, lyr["in_w"], cfg.rms_eps)
+            ops.gemm(a, lyr["qkv_w"], mode=L.VR_EPI_ROPE, positions=positions, rope_cos=self.rope_cos,
+                     rope_sin=self.rope_sin, rope_cols=2 * H, out=qkv)
+            ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=H, v_col0=2 * H, head_stride=64, head_dim=64, heads=nh, batch=B,
+                          cu_k=cu, max_k=max_len, cu_q=cu, max_q=max_len, causal=True, scale=cfg.head_dim ** -0.5, out=att)
+            ops.gemm(att, lyr["o_w"], resid=h, out=h, scale=s, out_dtype=torch.float32)
+            a = ops.rmsnorm(h, lyr["post_w"], cfg.rms_eps)
+            a = ops.gemm(a, lyr["gu_w"], mode=L.VR_EPI_SWIGLU)
+            ops.gemm(a, lyr["down_w"], resid=h, out=h, scale=s, out_dtype=torch.float32)
+        return h
+
+    # ------------------------------------------------------------------------------------------ end to end
+    def upload(self, pb: PreparedBatch):
+        """Host -> device copies of one prepared batch (pinned staging, async on the current stream)."""
+        dev = self.device
+
+        def up(a: np.ndarray) -> torch.Tensor:
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(dev, non_blocking=True)
+
+        groups = {k: up(v) for k, v in pb.groups.items()}
+        return groups, up(pb.token_src), up(pb.positions), up(pb.cu_seqlens)
+
+    def encode_prepared(self, pb: PreparedBatch, pooling: str = "wmean", normalize: bool = True,
+                        return_hidden: bool = False):
+        if pb.n_items == 0:
+            return torch.zeros((0, self.cfg.hidden), dtype=torch.float32, device=self.device)
+        if int(pb.seq_lens.max()) > self.cfg.max_pos:
+            raise ValueError(f"sequence longer than max_pos={self.cfg.max_pos}")
+        groups, src, pos, cu = self.upload(pb)
+        vision = self.encode_vision(groups, pb.group_row0, pb.n_slices)
+        h = self.lm_hidden(src, pos, cu, int(pb.seq_lens.max()), vision)
+        reps = ops.pool_norm(h, self.final_w, self.cfg.rms_eps, cu, pooling, normalize)
+        if return_hidden:
+            return reps, h
+        return reps
+
+    def encode(self, texts: Sequence[str], images: Sequence, tokenizer, max_inp_length: Optional[int] = 2048,
+               pooling: str = "wmean", normalize: bool = True) -> torch.Tensor:
+        """(texts, PIL images | None) -> fp32 device tensor [B, hidden], L2-normalised."""
+        pb = prepare_batch(texts, images, tokenizer, self.cfg, max_inp_length)
+        return self.encode_prepared(pb, pooling, normalize)

@@ -77,3 +77,74 @@ def gemm(
         )
     )
     return out
+
+
+def attention(
+    q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, q_col0: int, k_col0: int, v_col0: int, head_stride: int,
+    head_dim: int, heads: int, batch: int, cu_k: torch.Tensor, max_k: int, cu_q: Optional[torch.Tensor], max_q: int,
+    causal: bool, scale: float, out: torch.Tensor,
+) -> torch.Tensor:
+    """softmax(QK^T*scale)V on tcgen05; q/k/v are bf16 token matrices (see include/visrag_b200.h)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _bf16_2d(t, n)
+    if cu_k.dtype != torch.int32 or (cu_q is not None and cu_q.dtype != torch.int32):
+        raise ValueError("attention: cu_seqlens must be int32")
+    p = L.AttnParams()
+    p.q, p.ldq, p.q_rows = q.data_ptr(), q.stride(0), q.shape[0]
+    p.k, p.ldk = k.data_ptr(), k.stride(0)
+    p.v, p.ldv, p.kv_rows = v.data_ptr(), v.stride(0), k.shape[0]
+    p.q_col0, p.k_col0, p.v_col0 = q_col0, k_col0, v_col0
+    p.head_stride, p.head_dim, p.heads, p.batch = head_stride, head_dim, heads, batch
+    p.cu_q, p.cu_k = L.ptr(cu_q), cu_k.data_ptr()
+    p.max_q, p.max_k = max_q, max_k
+    p.causal, p.scale = int(causal), float(scale)
+    p.out, p.ldo = out.data_ptr(), out.stride(0)
+    L.check(L.lib().vr_attention(C.byref(p), L.stream_ptr()))
+    return out
+
+
+def im2col_norm(pixels: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
+    """uint8 [S,h,w,3] -> bf16 patch matrix [S*(h/p)*(w/p), ld_out] (normalised, zero padded columns)."""
+    if pixels.dtype != torch.uint8 or pixels.dim() != 4 or pixels.shape[3] != 3 or not pixels.is_contiguous():
+        raise ValueError("im2col_norm: expected contiguous uint8 [S,h,w,3]")
+    S, h, w, _ = pixels.shape
+    out = torch.empty((S * (h // patch) * (w // patch), ld_out), dtype=torch.bfloat16, device=pixels.device)
+    L.check(L.lib().vr_im2col_norm(pixels.data_ptr(), S, h, w, patch, out.data_ptr(), ld_out, L.stream_ptr()))
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, add: Optional[torch.Tensor] = None):
+    """fp32 [M,D] -> bf16 LN(x); with ``add`` [P,D] also returns LN(x)+add[row % P] (bf16)."""
+    M, D = x.shape
+    out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    out2 = torch.empty_like(out) if add is not None else None
+    L.check(L.lib().vr_layernorm(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps, M, D, out.data_ptr(),
+                                 out.stride(0), L.ptr(out2), L.ptr(add), 0 if add is None else add.shape[0], L.stream_ptr()))
+    return out if add is None else (out, out2)
+
+
+def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
+    M, D = x.shape
+    out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().vr_rmsnorm(x.data_ptr(), x.stride(0), gamma.data_ptr(), eps, M, D, out.data_ptr(), out.stride(0),
+                               L.stream_ptr()))
+    return out
+
+
+def build_lm_input(src: torch.Tensor, embed: torch.Tensor, scale_emb: float, vision: Optional[torch.Tensor]) -> torch.Tensor:
+    T, D = src.shape[0], embed.shape[1]
+    h = torch.empty((T, D), dtype=torch.float32, device=embed.device)
+    L.check(L.lib().vr_build_lm_input(src.data_ptr(), T, D, embed.data_ptr(), scale_emb, L.ptr(vision),
+                                      0 if vision is None else vision.stride(0), h.data_ptr(), h.stride(0), L.stream_ptr()))
+    return h
+
+
+POOLING = {"wmean": 0, "mean": 1, "lasttoken": 2, "cls": 3}
+
+
+def pool_norm(h: torch.Tensor, gamma: torch.Tensor, eps: float, cu: torch.Tensor, pooling: str, normalize: bool) -> torch.Tensor:
+    B = cu.shape[0] - 1
+    reps = torch.empty((B, h.shape[1]), dtype=torch.float32, device=h.device)
+    L.check(L.lib().vr_pool_norm(h.data_ptr(), h.stride(0), gamma.data_ptr(), eps, cu.data_ptr(), B, h.shape[1],
+                                 POOLING[pooling], int(normalize), reps.data_ptr(), L.stream_ptr()))
+    return reps
