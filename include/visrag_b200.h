@@ -131,6 +131,33 @@ int vr_build_lm_input(const int32_t* src, int32_t tokens, int32_t dim, const voi
 int vr_pool_norm(const float* h, int64_t ldh, const float* gamma, float eps, const int32_t* cu, int32_t batch, int32_t dim,
                  int32_t pooling, int32_t normalize, float* reps, void* stream);
 
+
+/* ------------------------------------------------------------------------------------
+ * Similarity + top-k: replaces `torch.matmul(Q, D^T)` + `torch.topk` of
+ * retriever/dense_retriever.py:25-30 (fp32 scores) and the Python merge loop `:88-92`.
+ * The [nq, nd] score matrix is never materialised:
+ *   vr_score_filter  : tcgen05 fp16 GEMM with a fused per-row running top-16 (per query block x doc range);
+ *   vr_score_rescore : exact fp32 rescoring of the survivors + top-k by (score desc, id asc) + a proof that
+ *                      nothing dropped could belong to the top-k (flags[q] = 1 when the proof fails; the caller
+ *                      then reruns that query through vr_score_exact + vr_topk_rows).
+ * Results are therefore exactly the fp32 top-k. Doc ids returned are `local index + id_offset`.
+ * ---------------------------------------------------------------------------------- */
+int vr_score_ranges(int32_t nq, int64_t nd);   /* doc ranges the filter uses: cand buffers are [nq, ranges*2*16] */
+int vr_score_list_len(void);                   /* 16 */
+int vr_f32_to_f16_rows(const float* src, int64_t rows, int32_t dim, void* dst_f16, float* norms, float* max_norm,
+                       void* stream);          /* norms / max_norm optional; *max_norm must be pre-zeroed */
+int vr_score_filter(const void* q_f16, int32_t nq, const void* d_f16, int64_t nd, int32_t dim, int32_t ranges,
+                    float* cand_scores, int32_t* cand_ids, void* stream);
+int vr_score_rescore(const float* q_f32, int32_t nq, const float* d_f32, int64_t nd, int32_t dim, int32_t ranges,
+                     const float* cand_scores, const int32_t* cand_ids, const float* max_doc_norm, int32_t k,
+                     int64_t id_offset, float* out_scores, int64_t* out_ids, int32_t* flags, void* stream);
+/* plain fp32 scan (small problems, flagged queries): scores [nq, nd] */
+int vr_score_exact(const float* q_f32, int32_t nq, const float* d_f32, int64_t nd, int32_t dim, float* scores, void* stream);
+/* top-k of every row of scores [rows, cols]; ids == NULL -> column index (+ id_offset), else ids[row, col]
+ * (negative ids are skipped): also the k-way merge of per-shard / per-rank partial top-k lists. */
+int vr_topk_rows(const float* scores, const int64_t* ids, int32_t rows, int64_t cols, int32_t k, int64_t id_offset,
+                 float* out_scores, int64_t* out_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

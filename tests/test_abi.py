@@ -1,0 +1,42 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/visrag_b200.h declares; argument
+validation (which happens before any CUDA call) reports errors through the status code + vr_last_error()."""
+import ctypes as C
+import os
+
+import pytest
+
+import __graft_entry__ as G
+from visrag_b200 import _lib as L
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(L.LIB_PATH):
+        G.build()
+    return L.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = G.exported_symbols()
+    assert len(syms) >= 15 and "vr_gemm" in syms and "vr_attention" in syms and "vr_score_filter" in syms
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.vr_abi_version() == 1
+
+
+def test_errors_are_status_codes_with_messages(lib):
+    e = L.GemmEpilogue()
+    rc = lib.vr_gemm(None, 0, None, 0, L.VR_BF16, 128, 128, 64, C.byref(e), None)
+    assert rc != 0 and b"null pointer" in lib.vr_last_error()
+    rc = lib.vr_im2col_norm(1, 1, 15, 14, 14, 1, 640, None)   # h not a multiple of the patch size
+    assert rc != 0 and b"bad geometry" in lib.vr_last_error()
+    rc = lib.vr_pool_norm(1, 8, 1, 1e-5, 1, 1, 8, 9, 1, 1, None)  # pooling id out of range
+    assert rc != 0 and b"pooling" in lib.vr_last_error()
+    assert lib.vr_score_list_len() == 16
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no fallback"):
+        L.lib()

@@ -1,0 +1,114 @@
+"""Encode-path parity on the B200: CUDA engine (through the C ABI and the reference-signature classes) against
+  (1) golden embeddings produced by the REAL reference (tests/golden/*.npz), tiny and full-size model,
+  (2) the oracle restatement on freshly seeded inputs, at the B1 (hidden states) and B2 (embeddings) boundaries.
+Stated tolerance (north_star: "within a stated fp tolerance"): cosine(embedding, fp32 reference) >= 0.999 per vector
+and max |diff| <= 4e-3 on unit vectors; top-k id sets identical on the golden (query, corpus) sets. The engine computes
+in bf16 operands / fp32 accumulate with fp32 residual streams; the reference run is fp32."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import QUERY_PREFIX, cosine_rows, load_case, synth_pages
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN, ABS_MAX = 0.999, 4e-3
+
+
+def _engine_model(cfg, sd, pooling="wmean"):
+    from visrag_b200.modeling import DRModelForInference, VisRAGRetB200
+
+    return DRModelForInference(lm_q=VisRAGRetB200(cfg, sd, "cuda:0"), pooling=pooling, normalize=True)
+
+
+def _items(texts, images, prefix):
+    return {"id": [f"{prefix}{i}" for i in range(len(texts))], "text": list(texts), "image": list(images)}
+
+
+def _check_case(name):
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    cfg, wseed, pages, queries, z = load_case(name)
+    sd = random_state_dict(cfg, wseed)
+    model = _engine_model(cfg, sd)
+    del sd
+    tok = StubTokenizer(cfg.vocab)
+    out = model(query=_items(queries, [None] * len(queries), "q"), passage=_items([""] * len(pages), pages, "d"),
+                tokenizer=tok, max_inp_length=2048)
+    assert out.p_reps.dtype == torch.float32 and out.p_reps.is_cuda
+    p, q = out.p_reps.cpu().numpy(), out.q_reps.cpu().numpy()
+    cp, cq = cosine_rows(p, z["page_reps"]), cosine_rows(q, z["query_reps"])
+    assert cp.min() >= COS_MIN and cq.min() >= COS_MIN, (cp, cq)
+    assert np.abs(p - z["page_reps"]).max() <= ABS_MAX and np.abs(q - z["query_reps"]).max() <= ABS_MAX
+    assert np.allclose(np.linalg.norm(p, axis=1), 1.0, atol=1e-5)
+    k = z["topk_indices"].shape[1]
+    top = np.argsort(-(q @ p.T), axis=1)[:, :k]
+    assert np.array_equal(np.sort(top, 1), np.sort(z["topk_indices"], 1))
+    return cp.min(), cq.min()
+
+
+def test_tiny_model_matches_reference_golden():
+    _check_case("tiny_v1")
+
+
+def test_full_size_model_matches_reference_golden():
+    """SigLIP-so400m (26 blocks) + Resampler + MiniCPM-2B (40 layers), 3.1 B parameters, vs the real reference's fp32 run."""
+    _check_case("full_v1")
+
+
+def test_boundaries_against_oracle_on_fresh_inputs():
+    from oracle import restated as O
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    cfg = VisRAGConfig.tiny()
+    sd = random_state_dict(cfg, 31337)
+    tok = StubTokenizer(cfg.vocab)
+    pages = synth_pages([(224, 224), (564 // 2, 3040 // 2), (1344, 1344), (336, 340)], 77)  # 1, 1+8, 1+9, 1 slices
+    texts = ["", "a caption", "", "x"]
+    model = _engine_model(cfg, sd)
+    # B2: pooled embeddings, all pooling modes the kernel implements
+    for pooling in ("wmean", "mean", "lasttoken", "cls"):
+        model.pooling = pooling
+        _, got = model.encode_passage(_items(texts, pages, "d"), tokenizer=tok, max_inp_length=2048)
+        want = O.encode(sd, cfg, tok, texts, pages, pooling=pooling)
+        c = cosine_rows(got.cpu().numpy(), want)
+        assert c.min() >= COS_MIN, (pooling, c)
+    # B1: right-padded final-norm hidden states + mask
+    out = model.lm_q(text=texts, image=pages, tokenizer=tok, max_inp_length=2048)
+    _, hid = O.encode(sd, cfg, tok, texts, pages, return_hidden=True)
+    assert out.last_hidden_state.shape[:2] == out.attention_mask.shape
+    for b, h in enumerate(hid):
+        n = int(out.attention_mask[b].sum())
+        assert n == h.shape[0]
+        got = out.last_hidden_state[b, :n].float().cpu().numpy()
+        assert np.abs(got - h).max() <= 0.05 * np.abs(h).max()
+        assert (out.last_hidden_state[b, n:] == 0).all()
+    # text-only queries incl. a 1-token-ish and a long one; empty batch
+    qs = [QUERY_PREFIX + "a", QUERY_PREFIX + " ".join(["word"] * 150)]
+    model.pooling = "wmean"
+    _, gq = model.encode_query(_items(qs, [None, None], "q"), tokenizer=tok, max_inp_length=2048)
+    assert cosine_rows(gq.cpu().numpy(), O.encode(sd, cfg, tok, qs, [None, None])).min() >= COS_MIN
+    assert model(query=None, passage=None).q_reps is None
+    # truncation at max_inp_length behaves like the reference (ids[:max])
+    _, gt = model.encode_query(_items(qs[1:], [None], "q"), tokenizer=tok, max_inp_length=40)
+    assert cosine_rows(gt.cpu().numpy(), O.encode(sd, cfg, tok, qs[1:], [None], max_inp_length=40)).min() >= COS_MIN
+
+
+def test_batch_composition_does_not_change_results():
+    """Same item alone vs inside a mixed batch: bit-identical (no padding, no cross-sequence leakage)."""
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.encoder import VisRAGEngine
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    cfg = VisRAGConfig.tiny()
+    eng = VisRAGEngine(cfg, random_state_dict(cfg, 5))
+    tok = StubTokenizer(cfg.vocab)
+    pages = synth_pages([(448, 448), (700, 900), (448, 448)], 9)
+    alone = eng.encode([""], [pages[1]], tok)
+    mixed = eng.encode(["", "", "query text", ""], [pages[0], pages[1], None, pages[2]], tok)
+    assert torch.equal(alone[0], mixed[1])
+    assert eng.encode([], [], tok).shape == (0, cfg.hidden)

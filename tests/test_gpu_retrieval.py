@@ -1,0 +1,121 @@
+"""Similarity + top-k on the B200 against the oracle's fp32 scan: ids bit-identical (tie rule: score desc, id asc),
+scores within fp32 summation-order noise (2e-6 on unit vectors)."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restated as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit(rs, n, d):
+    x = rs.randn(n, d).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def _run(Q, D, k, **kw):
+    from visrag_b200 import retriever as R
+
+    idx = R.build_index(D)
+    stats = {}
+    s, i = R.score_topk(torch.from_numpy(Q).cuda(), idx, k, stats=stats, **kw)
+    return s.cpu().numpy(), i.cpu().numpy(), stats
+
+
+@pytest.mark.parametrize("nq,nd,d,k", [(300, 5000, 256, 10), (1000, 10000, 2304, 10), (129, 4097, 2304, 5), (4, 32, 256, 5),
+                                       (2049, 20000, 64, 16), (1, 100000, 128, 10)])
+def test_topk_equals_fp32_scan(nq, nd, d, k):
+    rs = np.random.RandomState(nq + nd)
+    Q, D = _unit(rs, nq, d), _unit(rs, nd, d)
+    s, i, stats = _run(Q, D, k)
+    s_ref, i_ref = O.score_topk(Q, D, k)
+    assert np.array_equal(i, i_ref), stats
+    assert np.abs(s - s_ref).max() <= 2e-6
+    if nq * nd > (1 << 22) and nd >= 256:
+        assert stats["path"] == "filter+rescore"
+
+
+def test_ties_duplicates_and_short_corpus():
+    rs = np.random.RandomState(3)
+    base = _unit(rs, 3000, 128)
+    D = np.concatenate([base, base[:500]])          # 500 exact duplicates -> exact score ties
+    Q = _unit(rs, 2000, 128)
+    s, i, stats = _run(Q, D, 10)
+    s_ref, i_ref = O.score_topk(Q, D, 10)
+    assert np.array_equal(i, i_ref) and stats["path"] == "filter+rescore"
+    # k > nd: tail is (-inf, -1)
+    s, i, _ = _run(Q[:3], D[:4], 6)
+    assert (i[:, 4:] == -1).all() and np.isinf(s[:, 4:]).all() and np.array_equal(i[:, :4], O.score_topk(Q[:3], D[:4], 4)[1])
+
+
+def test_clustered_corpus_takes_the_exact_fallback_and_stays_correct():
+    """More than 16 near-identical relevant docs inside one doc range defeat the per-range top-16 filter; the proof
+    step must notice (flag) and the fp32 fallback must still return the exact answer."""
+    rs = np.random.RandomState(4)
+    d = 128
+    D = _unit(rs, 40000, d)
+    Q = _unit(rs, 1500, d)
+    for qi in range(20):                              # plant 40 docs within 1e-4 of query qi, all in one 256-doc tile
+        noise = rs.randn(40, d).astype(np.float32) * 1e-4
+        D[5000:5040] = (Q[qi] + noise) / np.linalg.norm(Q[qi] + noise, axis=1, keepdims=True) if qi == 0 else D[5000:5040]
+    s, i, stats = _run(Q, D, 10)
+    s_ref, i_ref = O.score_topk(Q, D, 10)
+    assert stats["flagged"] >= 1
+    assert np.array_equal(i, i_ref) and np.abs(s - s_ref).max() <= 2e-6
+    s2, i2, st2 = _run(Q[:50], D, 10, force_exact=True)
+    assert st2["path"] == "exact" and np.array_equal(i2, i_ref[:50])
+
+
+def test_large_problem_sets_match_torch_fp32():
+    """BASELINE config-3 scale (1 k x 10 k x 2304) and a 200 k corpus: compare with torch fp32 matmul + topk on the GPU."""
+    from visrag_b200 import retriever as R
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for nq, nd in ((1000, 10000), (512, 200000)):
+        Dm = torch.nn.functional.normalize(torch.randn(nd, 2304, device="cuda", generator=g), dim=1)
+        Qm = torch.nn.functional.normalize(torch.randn(nq, 2304, device="cuda", generator=g), dim=1)
+        idx = R.build_index(Dm)
+        s, i = R.score_topk(Qm, idx, 10)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ts, ti = torch.topk(Qm @ Dm.T, 10, dim=1)
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        assert torch.equal(torch.sort(i, 1).values, torch.sort(ti, 1).values)
+        assert (s - ts).abs().max().item() <= 5e-6
+
+
+def test_reference_signature_drop_ins(tmp_path):
+    from visrag_b200 import retriever as R
+
+    rs = np.random.RandomState(8)
+    D, Q = _unit(rs, 700, 256), _unit(rs, 9, 256)
+    out = str(tmp_path)
+    R.save_shard(os.path.join(out, "embeddings.corpus.rank.0.0-400"), D[:400], [f"d{i}" for i in range(400)])
+    R.save_shard(os.path.join(out, "embeddings.corpus.rank.1.0-300"), D[400:], [f"d{i}" for i in range(400, 700)])
+    R.save_shard(os.path.join(out, "embeddings.query.rank.0"), Q, [f"q{i}" for i in range(9)])
+    s, i, lookup = R._retrieve_one_shard(os.path.join(out, "embeddings.corpus.rank.0.0-400"), torch.from_numpy(Q).cuda(), 5, "cuda:0")
+    assert s.shape == (9, 5) and i.dtype == torch.int64 and lookup[3] == "d3"
+    assert np.array_equal(i.cpu().numpy(), O.score_topk(Q, D[:400], 5)[1])
+    res = R.distributed_parallel_retrieve(SimpleNamespace(output_dir=out, process_index=0, device="cuda:0"), 5)
+    assert set(res) == {f"q{i}" for i in range(9)}
+    _, gi = O.score_topk(Q, D, 5)
+    for qn in range(9):
+        run = sorted(res[f"q{qn}"].items(), key=lambda kv: (-kv[1], kv[0]))
+        assert len(run) == 10                                    # union of two shards' top-5, like the reference
+        assert {int(x[0][1:]) for x in run[:5]} == set(gi[qn].tolist())
+
+
+def test_merge_topk_kernel():
+    from visrag_b200 import retriever as R
+
+    rs = np.random.RandomState(2)
+    s = rs.randn(50, 24).astype(np.float32)
+    i = np.stack([rs.permutation(1000)[:24] for _ in range(50)]).astype(np.int64)
+    i[:, 20:] = -1
+    ms, mi = R.merge_topk(torch.from_numpy(s).cuda(), torch.from_numpy(i).cuda(), 7)
+    ws, wi = O.merge_topk([(s[:, :20], i[:, :20])], 7)
+    assert np.array_equal(mi.cpu().numpy(), wi) and np.allclose(ms.cpu().numpy(), ws)

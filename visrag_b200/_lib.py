@@ -77,6 +77,20 @@ def _declare(lib: C.CDLL) -> None:
     lib.vr_rmsnorm.argtypes = [vp, i64, vp, f32, i32, i32, vp, i64, vp]
     lib.vr_build_lm_input.restype = i32
     lib.vr_build_lm_input.argtypes = [vp, i32, i32, vp, f32, vp, i64, vp, i64, vp]
+    lib.vr_score_ranges.restype = i32
+    lib.vr_score_ranges.argtypes = [i32, i64]
+    lib.vr_score_list_len.restype = i32
+    lib.vr_score_list_len.argtypes = []
+    lib.vr_f32_to_f16_rows.restype = i32
+    lib.vr_f32_to_f16_rows.argtypes = [vp, i64, i32, vp, vp, vp, vp]
+    lib.vr_score_filter.restype = i32
+    lib.vr_score_filter.argtypes = [vp, i32, vp, i64, i32, i32, vp, vp, vp]
+    lib.vr_score_rescore.restype = i32
+    lib.vr_score_rescore.argtypes = [vp, i32, vp, i64, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp, vp]
+    lib.vr_score_exact.restype = i32
+    lib.vr_score_exact.argtypes = [vp, i32, vp, i64, i32, vp, vp]
+    lib.vr_topk_rows.restype = i32
+    lib.vr_topk_rows.argtypes = [vp, vp, i32, i64, i32, i64, vp, vp, vp]
     lib.vr_pool_norm.restype = i32
     lib.vr_pool_norm.argtypes = [vp, i64, vp, f32, vp, i32, i32, i32, i32, vp, vp]
 
@@ -95,7 +109,12 @@ def lib() -> C.CDLL:
     return _lib
 
 
+LAUNCHES = 0  # number of library kernel launches issued (bench.py reports it as gpu_launches)
+
+
 def check(rc: int) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         raise RuntimeError(f"visrag_b200: {lib().vr_last_error().decode()} (status {rc})")
 

@@ -51,8 +51,9 @@ class VisRAGEngine:
             # ---- ViT
             P2 = 3 * cfg.patch_size ** 2
             self.patch_k = ((P2 + 63) // 64) * 64  # 588 -> 640: TMA rows must be 16-byte multiples
-            w = torch.zeros((D, self.patch_k), dtype=torch.float32)
-            w[:, :P2] = sd["vpm.patch_embed.proj.weight"].float().reshape(D, P2).cpu()
+            pw = sd["vpm.patch_embed.proj.weight"].float().reshape(D, P2)
+            w = torch.zeros((D, self.patch_k), dtype=torch.float32, device=pw.device)
+            w[:, :P2] = pw
             self.patch_w = _bf16(w, dev)
             self.patch_b = _f32(sd["vpm.patch_embed.proj.bias"], dev)
             self.pos_embed = sd["vpm.pos_embed"].float().cpu()
@@ -61,10 +62,10 @@ class VisRAGEngine:
             self.blocks = []
             for i in range(cfg.vit_depth):
                 p = f"vpm.blocks.{i}."
-                wq = sd[p + "attn.qkv.weight"].float().cpu().reshape(3, nh, hd, D)
-                bq = sd[p + "attn.qkv.bias"].float().cpu().reshape(3, nh, hd)
-                wpad = torch.zeros((3, nh, hs, D))
-                bpad = torch.zeros((3, nh, hs))
+                wq = sd[p + "attn.qkv.weight"].float().reshape(3, nh, hd, D)
+                bq = sd[p + "attn.qkv.bias"].float().reshape(3, nh, hd)
+                wpad = torch.zeros((3, nh, hs, D), device=wq.device)
+                bpad = torch.zeros((3, nh, hs), device=wq.device)
                 wpad[:, :, :hd] = wq
                 bpad[:, :, :hd] = bq
                 self.blocks.append(dict(
