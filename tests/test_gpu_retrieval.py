@@ -59,9 +59,9 @@ def test_clustered_corpus_takes_the_exact_fallback_and_stays_correct():
     d = 128
     D = _unit(rs, 40000, d)
     Q = _unit(rs, 1500, d)
-    for qi in range(20):                              # plant 40 docs within 1e-4 of query qi, all in one 256-doc tile
-        noise = rs.randn(40, d).astype(np.float32) * 1e-4
-        D[5000:5040] = (Q[qi] + noise) / np.linalg.norm(Q[qi] + noise, axis=1, keepdims=True) if qi == 0 else D[5000:5040]
+    for qi in range(5):                               # 40 docs within ~1e-4 of query qi, all inside one doc tile
+        pert = Q[qi] + rs.randn(40, d).astype(np.float32) * 1e-5
+        D[5000 + 300 * qi: 5040 + 300 * qi] = pert / np.linalg.norm(pert, axis=1, keepdims=True)
     s, i, stats = _run(Q, D, 10)
     s_ref, i_ref = O.score_topk(Q, D, 10)
     assert stats["flagged"] >= 1
