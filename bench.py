@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the VisRAG-Ret hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one JSON line from rank 0)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+Workload = BASELINE.json configs[2]: full VisRAG-Ret (SigLIP-so400m 26 blocks + Resampler + MiniCPM-2B 40 layers,
+random-init weights of that architecture) encoding synthetic 448x448 pages, plus 1 k text queries scored top-10
+against a 10 k-page corpus. One step = one batch of `--pages` pages through the whole encode path.
+  value : pages/s, inputs (uint8 pixels + packed token arrays) already resident in HBM, CUDA-event timed, max over ranks
+  e2e   : pages/s through the reference-signature API DRModelForInference(passage=...) with HOST inputs (PIL pages):
+          host prep + pinned H2D + kernels + D2H of the embeddings, every step
+N > 1: one process per GPU (torchrun); every rank encodes its own `--pages` pages per step (weak scaling, no collective
+in the encode path); the retrieval figure shards the corpus by page and merges partial top-k with one all-gather.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "page-images encoded/sec"
+UNIT = "pages/s"
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1429.0), d.get("hbm_gbs", 6585.8), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (recipe in B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/vr_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_gemm_flops_per_page(n_patches: int, lm_tokens: int) -> float:
+    """Dense-contraction FLOPs one page needs, GEMMs only (attention excluded), UNPADDED dims."""
+    vit = 793_046_016.0 * n_patches                       # patch-embed + 26 x (qkv, proj, fc1, fc2)
+    rs = (5_308_416.0 + 21_233_664.0) * n_patches + 2 * 2 * 64 * 2304 * 2304  # kv_proj, Wk, Wv per token; out-proj + proj on 64 rows
+    lm = 4_883_742_720.0 * lm_tokens
+    return vit + rs + lm
+
+
+def total_flops_per_page(n_patches: int, lm_tokens: int) -> float:
+    return (793_046_016.0 * n_patches + 119_808.0 * n_patches ** 2 + 27_131_904.0 * n_patches + 2.0385e9
+            + 4_883_742_720.0 * lm_tokens + 184_320.0 * lm_tokens ** 2)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from PIL import Image
+
+    from visrag_b200 import _lib as L
+    from visrag_b200 import ops, retriever
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.host import prepare_batch
+    from visrag_b200.modeling import DRModelForInference, VisRAGRetB200
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict_device
+
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    cfg = VisRAGConfig.full() if a.model == "full" else VisRAGConfig.tiny()
+    tok = StubTokenizer(cfg.vocab)
+    t0 = time.time()
+    sd = random_state_dict_device(cfg, 2024 + rank, dev)
+    lm = VisRAGRetB200(cfg, sd, dev)
+    eng = lm.engine
+    model = DRModelForInference(lm_q=lm, pooling="wmean", normalize=True)
+    if not (rank == 0 and world == 1 and a.cpu_baseline):
+        del sd
+    torch.cuda.empty_cache()
+    setup_s = time.time() - t0
+
+    # ---- synthetic pages: uint8 448x448 noise (single slice, 1024 patches, 68 LM tokens)
+    P = a.pages
+    rs = np.random.RandomState(1000 + rank)
+    page_arrays = rs.randint(0, 256, (P, a.page_px, a.page_px, 3), dtype=np.uint8)
+    pages = [Image.fromarray(x) for x in page_arrays]
+    items = {"id": [f"d{i}" for i in range(P)], "text": [""] * P, "image": pages}
+    pb = prepare_batch(items["text"], pages, tok, cfg, 2048)
+    groups, src, pos, cu = eng.upload(pb)
+    max_len = int(pb.seq_lens.max())
+    n_patches = (a.page_px // 14) ** 2 if a.page_px % 14 == 0 else None
+    lm_tokens = float(pb.seq_lens.mean())
+
+    def step_device():
+        return eng.encode_device(groups, pb.group_row0, pb.n_slices, src, pos, cu, max_len)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident throughput
+    for _ in range(a.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        reps = step_device()
+    e1.record()
+    barrier()
+    launches = L.LAUNCHES - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = world * a.steps * P / (ms_total / 1e3)
+
+    # ---- (2) end to end through the reference-signature API: host PIL pages -> device -> embeddings on host
+    for _ in range(max(1, a.warmup - 1)):
+        model(passage=items, tokenizer=tok, max_inp_length=2048).p_reps.cpu()
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        host_reps = model(passage=items, tokenizer=tok, max_inp_length=2048).p_reps.cpu()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * a.steps * P / (e2e_ms / 1e3)
+    h2d = int(sum(v.nbytes for v in pb.groups.values()) + pb.token_src.nbytes + pb.positions.nbytes + pb.cu_seqlens.nbytes)
+    d2h = int(host_reps.numel() * 4)
+    assert torch.isfinite(host_reps).all()
+
+    # ---- (3) roofline pass: CUDA events around every launch (separate from the timed regions above)
+    ops.profile_begin()
+    for _ in range(2):
+        step_device()
+    prof = ops.profile_end()
+    peak_tf, peak_hbm, peak_src = load_peaks()
+    gemm_n, gemm_ms, gemm_padded_flops = prof.get("gemm", (0, 0.0, 0.0))
+    all_ms = sum(v[1] for v in prof.values())
+    roofline, shares = None, {}
+    if gemm_n and n_patches:
+        alg = algorithmic_gemm_flops_per_page(n_patches, lm_tokens) * P * 2  # two profiled steps
+        achieved = alg / (gemm_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogue variants)", "achieved": round(achieved, 1),
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None,
+                    "peak_source": peak_src, "launches_per_step": gemm_n // 2, "avg_launch_ms": round(gemm_ms / gemm_n, 4),
+                    "padded_tflops": round(gemm_padded_flops / (gemm_ms / 1e3) / 1e12, 1)}
+        shares = {k: round(v[1] / all_ms, 4) for k, v in sorted(prof.items())}
+
+    # ---- (4) queries: encode text queries + exact top-10 over a page-sharded corpus
+    nq, nd = a.queries, a.corpus
+    from visrag_b200.synth import synth_queries
+    qtexts = synth_queries(nq, 7)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    lo, hi = retriever.shard_range(nd * world, rank, world)
+    corpus = torch.nn.functional.normalize(torch.randn(hi - lo, cfg.hidden, device=dev, generator=g), dim=1)
+    index = retriever.build_index(corpus)
+    qb = a.query_batch
+
+    def queries_step():
+        outs = []
+        for i in range(0, nq, qb):
+            outs.append(eng.encode(qtexts[i:i + qb], [None] * len(qtexts[i:i + qb]), tok))
+        qe = torch.cat(outs)
+        s, ids = retriever.sharded_topk(qe, index, 10, lo)
+        return s.cpu(), ids.cpu()
+
+    queries_step()
+    barrier()
+    e0.record()
+    for _ in range(a.query_reps):
+        s_top, i_top = queries_step()
+    e1.record()
+    barrier()
+    q_ms = max_over_ranks(e0.elapsed_time(e1)) / a.query_reps
+    qe = torch.nn.functional.normalize(torch.randn(nq, cfg.hidden, device=dev, generator=g), dim=1)
+    retriever.sharded_topk(qe, index, 10, lo)
+    barrier()
+    e0.record()
+    for _ in range(a.query_reps):
+        retriever.sharded_topk(qe, index, 10, lo)
+    e1.record()
+    barrier()
+    r_ms = max_over_ranks(e0.elapsed_time(e1)) / a.query_reps
+
+    # ---- (5) CPU baseline: the oracle port of the reference algorithm on the host cores (rank 0, N = 1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and a.cpu_baseline:
+        cpu_baseline = cpu_port_baseline(cfg, {k: v.float().cpu() for k, v in sd.items()}, tok, pages[: a.cpu_pages], a.page_px)
+        del sd
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2]: full VisRAG-Ret (SigLIP-so400m x26 + Resampler + MiniCPM-2B x40) encode of "
+                                   f"synthetic {a.page_px}x{a.page_px} pages; {nq} text queries top-10 over {nd * world} pages",
+                       "model": a.model, "pages_per_step_per_gpu": P, "global_batch": P * world, "patches_per_page": n_patches,
+                       "lm_tokens_per_page": lm_tokens, "parallelism": f"dp{world} (pages sharded, no encode collective)",
+                       "weights": "random-init, bf16", "l2": "working set (6.3 GB weights + >1 GB activations per step) >> 126 MB L2"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms / a.steps, 3), "api": "DRModelForInference.forward(passage=..., tokenizer=...)"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "kernel_time_share": shares,
+            "model_tflops": round(total_flops_per_page(n_patches, lm_tokens) * value / 1e12 / world, 1) if n_patches else None,
+            "queries": {"queries_per_s_encode_plus_top10": round(nq / (q_ms / 1e3), 1), "retrieve_only_queries_per_s": round(nq / (r_ms / 1e3), 1),
+                        "n_queries": nq, "corpus_pages": nd * world, "k": 10, "collective": "1 all_gather of [nq,10] (score,id)" if world > 1 else None},
+            "cpu_baseline": cpu_baseline, "setup_s": round(setup_s, 1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_port_baseline(cfg, sd_cpu, tok, pages, page_px):
+    """Times oracle/restated.py (the CPU port of the reference algorithm) on a bounded sample of the same workload."""
+    import torch
+
+    from oracle import restated as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.time()
+    O.encode(sd_cpu, cfg, tok, [""] * len(pages), pages)
+    dt = time.time() - t0
+    return {"value": round(len(pages) / dt, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(pages)} pages {page_px}x{page_px}, full model, fp32, oracle/restated.py", "seconds": round(dt, 1)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    """The reference's algorithm on the host cores. The reference itself is pure Python over PyTorch and cannot travel to
+    the GPU box (/root/reference is absent there), so this runs its oracle port (validated against the real reference in the
+    build container, tests/golden). Each step = ONE page through the full model; rank 0 only."""
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from oracle import restated as O
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict, random_state_dict_device
+
+    cfg = VisRAGConfig.full() if a.model == "full" else VisRAGConfig.tiny()
+    tok = StubTokenizer(cfg.vocab)
+    if torch.cuda.is_available():  # draw the 3.1 B weights on the GPU (seconds) and move them to the host; compute stays on the CPU
+        sd = {k: v.float().cpu() for k, v in random_state_dict_device(cfg, 2024, "cuda:0").items()}
+    else:
+        sd = random_state_dict(cfg, 2024)
+    torch.set_num_threads(os.cpu_count() or 1)
+    rs = np.random.RandomState(1000)
+    n = a.steps + a.warmup
+    pages = [Image.fromarray(rs.randint(0, 256, (a.page_px, a.page_px, 3), dtype=np.uint8)) for _ in range(n)]
+    for i in range(a.warmup):
+        O.encode(sd, cfg, tok, [""], [pages[i]])
+    t0 = time.time()
+    for i in range(a.warmup, n):
+        O.encode(sd, cfg, tok, [""], [pages[i]])
+    dt = time.time() - t0
+    v = a.steps / dt
+    sample = f"{a.steps} steps x 1 page {a.page_px}x{a.page_px}, full model fp32 on host cores"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[2]: full VisRAG-Ret encode of synthetic {a.page_px}x{a.page_px} pages", "model": a.model},
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="full", choices=["full", "tiny"])
+    ap.add_argument("--pages", type=int, default=128, help="pages per step per GPU")
+    ap.add_argument("--page-px", type=int, default=448)
+    ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--corpus", type=int, default=10000, help="corpus pages per GPU for the retrieval figure")
+    ap.add_argument("--query-batch", type=int, default=500)
+    ap.add_argument("--query-reps", type=int, default=3)
+    ap.add_argument("--cpu-pages", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "ours":
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

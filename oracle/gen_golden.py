@@ -22,20 +22,7 @@ warnings.filterwarnings("ignore")
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-QUERY_PREFIX = "Represent this query for retrieving relevant documents: "  # eval.sh:45
-
-
-def synth_pages(sizes, seed):
-    """uint8 RGB noise pages; numpy's legacy RandomState stream is stable across versions."""
-    rs = np.random.RandomState(seed)
-    return [Image.fromarray(rs.randint(0, 256, (h, w, 3), dtype=np.uint8)) for (w, h) in sizes]
-
-
-def synth_queries(n, seed):
-    rs = np.random.RandomState(seed)
-    vocab = ["revenue", "table", "figure", "growth", "policy", "network", "energy", "chart", "model", "summary",
-             "annual", "report", "risk", "market", "climate", "protein", "budget", "survey", "method", "result"]
-    return [QUERY_PREFIX + " ".join(vocab[j] for j in rs.randint(0, len(vocab), rs.randint(3, 12))) for _ in range(n)]
+from visrag_b200.synth import QUERY_PREFIX, synth_pages, synth_queries  # noqa: E402,F401
 
 
 def geometry_cases():

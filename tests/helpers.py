@@ -7,12 +7,7 @@ from PIL import Image
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-QUERY_PREFIX = "Represent this query for retrieving relevant documents: "
-
-
-def synth_pages(sizes, seed):
-    rs = np.random.RandomState(seed)
-    return [Image.fromarray(rs.randint(0, 256, (int(h), int(w), 3), dtype=np.uint8)) for (w, h) in sizes]
+from visrag_b200.synth import QUERY_PREFIX, synth_pages  # noqa: E402,F401
 
 
 def load_case(name):

@@ -30,8 +30,9 @@ def stage_elementwise():
     dev = "cuda"
     px = torch.randint(0, 256, (3, 28, 42, 3), dtype=torch.uint8, device=dev)
     got = ops.im2col_norm(px, 14, 640)
-    x = ((px.float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2)  # [S,3,h,w]
-    want = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    # reference arithmetic on the CPU like torchvision's ToTensor/Normalize (true division; CUDA torch divides by reciprocal)
+    x = ((px.cpu().float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2)  # [S,3,h,w]
+    want = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588).to(dev)
     ok &= report("im2col", got[:, :588], want.bfloat16(), 1e-6)
     ok &= report("im2col pad", got[:, 588:], torch.zeros_like(got[:, 588:]), 1e-6)
     for D in (288, 1152, 2304):

@@ -217,15 +217,37 @@ class VisRAGEngine:
         return h
 
     # ------------------------------------------------------------------------------------------ end to end
+    def _stage(self, a: np.ndarray, key) -> torch.Tensor:
+        """numpy -> device through a persistent (grow-only) pinned staging buffer identified by `key`."""
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+            buf = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+            self._pinned[key] = buf
+        stage = buf[: t.numel()].view(t.shape)
+        stage.copy_(t)
+        return stage.to(self.device, non_blocking=True)
+
     def upload(self, pb: PreparedBatch):
-        """Host -> device copies of one prepared batch (pinned staging, async on the current stream)."""
-        dev = self.device
+        """Host -> device copies of one prepared batch: pinned staging, async on the current stream. The staging
+        buffers are reused, so the previous upload's copies are waited for first (they finished long ago)."""
+        if not hasattr(self, "_pinned"):
+            self._pinned, self._upload_done = {}, None
+        if self._upload_done is not None:
+            self._upload_done.synchronize()
+        groups = {k: self._stage(v, ("px", k)) for k, v in pb.groups.items()}
+        out = groups, self._stage(pb.token_src, "src"), self._stage(pb.positions, "pos"), self._stage(pb.cu_seqlens, "cu")
+        self._upload_done = torch.cuda.Event()
+        self._upload_done.record()
+        return out
 
-        def up(a: np.ndarray) -> torch.Tensor:
-            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(dev, non_blocking=True)
-
-        groups = {k: up(v) for k, v in pb.groups.items()}
-        return groups, up(pb.token_src), up(pb.positions), up(pb.cu_seqlens)
+    def encode_device(self, groups, group_row0, n_slices: int, src, pos, cu, max_len: int, pooling: str = "wmean",
+                      normalize: bool = True, return_hidden: bool = False):
+        """Inputs already in HBM -> pooled embeddings [B, hidden] fp32 (the device-resident hot path)."""
+        vision = self.encode_vision(groups, group_row0, n_slices)
+        h = self.lm_hidden(src, pos, cu, max_len, vision)
+        reps = ops.pool_norm(h, self.final_w, self.cfg.rms_eps, cu, pooling, normalize)
+        return (reps, h) if return_hidden else reps
 
     def encode_prepared(self, pb: PreparedBatch, pooling: str = "wmean", normalize: bool = True,
                         return_hidden: bool = False):
@@ -234,12 +256,8 @@ class VisRAGEngine:
         if int(pb.seq_lens.max()) > self.cfg.max_pos:
             raise ValueError(f"sequence longer than max_pos={self.cfg.max_pos}")
         groups, src, pos, cu = self.upload(pb)
-        vision = self.encode_vision(groups, pb.group_row0, pb.n_slices)
-        h = self.lm_hidden(src, pos, cu, int(pb.seq_lens.max()), vision)
-        reps = ops.pool_norm(h, self.final_w, self.cfg.rms_eps, cu, pooling, normalize)
-        if return_hidden:
-            return reps, h
-        return reps
+        return self.encode_device(groups, pb.group_row0, pb.n_slices, src, pos, cu, int(pb.seq_lens.max()), pooling,
+                                  normalize, return_hidden)
 
     def encode(self, texts: Sequence[str], images: Sequence, tokenizer, max_inp_length: Optional[int] = 2048,
                pooling: str = "wmean", normalize: bool = True) -> torch.Tensor:

@@ -9,6 +9,37 @@ import torch
 
 from . import _lib as L
 
+_PROF = None  # list of (kind, start_event, end_event, flops) while profiling is on
+
+
+def profile_begin() -> None:
+    """Start recording one CUDA-event pair around every kernel launch (bench.py's roofline pass)."""
+    global _PROF
+    _PROF = []
+
+
+def profile_end():
+    """Stop recording; returns {kind: (launches, total_ms, total_flops)} (synchronises the device)."""
+    global _PROF
+    rec, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, e0, e1, flops in rec or []:
+        n, ms, fl = out.get(kind, (0, 0.0, 0.0))
+        out[kind] = (n + 1, ms + e0.elapsed_time(e1), fl + flops)
+    return out
+
+
+def _launch(kind: str, flops: float, fn, *args) -> None:
+    if _PROF is None:
+        L.check(fn(*args))
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(fn(*args))
+    e1.record()
+    _PROF.append((kind, e0, e1, flops))
+
 
 def _bf16_2d(t: torch.Tensor, name: str) -> None:
     if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
@@ -71,11 +102,8 @@ def gemm(
     e.rope_cols = rope_cols
     e.out = out.data_ptr()
     e.ldo = out.stride(0)
-    L.check(
-        L.lib().vr_gemm_tuned(
-            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.VR_BF16, M, N, K, C.byref(e), block_n, L.stream_ptr()
-        )
-    )
+    _launch("gemm", 2.0 * M * N * K, L.lib().vr_gemm_tuned, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.VR_BF16,
+            M, N, K, C.byref(e), block_n, L.stream_ptr())
     return out
 
 
@@ -99,7 +127,7 @@ def attention(
     p.max_q, p.max_k = max_q, max_k
     p.causal, p.scale = int(causal), float(scale)
     p.out, p.ldo = out.data_ptr(), out.stride(0)
-    L.check(L.lib().vr_attention(C.byref(p), L.stream_ptr()))
+    _launch("attention", 0.0, L.lib().vr_attention, C.byref(p), L.stream_ptr())
     return out
 
 
@@ -109,7 +137,7 @@ def im2col_norm(pixels: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
         raise ValueError("im2col_norm: expected contiguous uint8 [S,h,w,3]")
     S, h, w, _ = pixels.shape
     out = torch.empty((S * (h // patch) * (w // patch), ld_out), dtype=torch.bfloat16, device=pixels.device)
-    L.check(L.lib().vr_im2col_norm(pixels.data_ptr(), S, h, w, patch, out.data_ptr(), ld_out, L.stream_ptr()))
+    _launch("im2col", 0.0, L.lib().vr_im2col_norm, pixels.data_ptr(), S, h, w, patch, out.data_ptr(), ld_out, L.stream_ptr())
     return out
 
 
@@ -118,24 +146,24 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     M, D = x.shape
     out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
     out2 = torch.empty_like(out) if add is not None else None
-    L.check(L.lib().vr_layernorm(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps, M, D, out.data_ptr(),
-                                 out.stride(0), L.ptr(out2), L.ptr(add), 0 if add is None else add.shape[0], L.stream_ptr()))
+    _launch("norm", 0.0, L.lib().vr_layernorm, x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps, M, D,
+            out.data_ptr(), out.stride(0), L.ptr(out2), L.ptr(add), 0 if add is None else add.shape[0], L.stream_ptr())
     return out if add is None else (out, out2)
 
 
 def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
     M, D = x.shape
     out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib().vr_rmsnorm(x.data_ptr(), x.stride(0), gamma.data_ptr(), eps, M, D, out.data_ptr(), out.stride(0),
-                               L.stream_ptr()))
+    _launch("norm", 0.0, L.lib().vr_rmsnorm, x.data_ptr(), x.stride(0), gamma.data_ptr(), eps, M, D, out.data_ptr(),
+            out.stride(0), L.stream_ptr())
     return out
 
 
 def build_lm_input(src: torch.Tensor, embed: torch.Tensor, scale_emb: float, vision: Optional[torch.Tensor]) -> torch.Tensor:
     T, D = src.shape[0], embed.shape[1]
     h = torch.empty((T, D), dtype=torch.float32, device=embed.device)
-    L.check(L.lib().vr_build_lm_input(src.data_ptr(), T, D, embed.data_ptr(), scale_emb, L.ptr(vision),
-                                      0 if vision is None else vision.stride(0), h.data_ptr(), h.stride(0), L.stream_ptr()))
+    _launch("other", 0.0, L.lib().vr_build_lm_input, src.data_ptr(), T, D, embed.data_ptr(), scale_emb, L.ptr(vision),
+            0 if vision is None else vision.stride(0), h.data_ptr(), h.stride(0), L.stream_ptr())
     return h
 
 
@@ -145,6 +173,6 @@ POOLING = {"wmean": 0, "mean": 1, "lasttoken": 2, "cls": 3}
 def pool_norm(h: torch.Tensor, gamma: torch.Tensor, eps: float, cu: torch.Tensor, pooling: str, normalize: bool) -> torch.Tensor:
     B = cu.shape[0] - 1
     reps = torch.empty((B, h.shape[1]), dtype=torch.float32, device=h.device)
-    L.check(L.lib().vr_pool_norm(h.data_ptr(), h.stride(0), gamma.data_ptr(), eps, cu.data_ptr(), B, h.shape[1],
-                                 POOLING[pooling], int(normalize), reps.data_ptr(), L.stream_ptr()))
+    _launch("other", 0.0, L.lib().vr_pool_norm, h.data_ptr(), h.stride(0), gamma.data_ptr(), eps, cu.data_ptr(), B, h.shape[1],
+            POOLING[pooling], int(normalize), reps.data_ptr(), L.stream_ptr())
     return reps
