@@ -280,12 +280,38 @@ def cpu_port_baseline(cfg, sd_cpu, tok, pages, page_px):
 
     from oracle import restated as O
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    t0 = time.time()
-    O.encode(sd_cpu, cfg, tok, [""] * len(pages), pages)
+    threads = pick_cpu_threads()
+    torch.set_num_threads(threads)
+    t0, done = time.time(), 0
+    for pg in pages:  # bounded sample: stop after ~25 s of CPU work
+        O.encode(sd_cpu, cfg, tok, [""], [pg])
+        done += 1
+        if time.time() - t0 > 25.0:
+            break
     dt = time.time() - t0
-    return {"value": round(len(pages) / dt, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(pages)} pages {page_px}x{page_px}, full model, fp32, oracle/restated.py", "seconds": round(dt, 1)}
+    return {"value": round(done / dt, 4), "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{done} pages {page_px}x{page_px}, full model, fp32, oracle/restated.py", "seconds": round(dt, 1)}
+
+
+def pick_cpu_threads():
+    """All host threads is not the fastest setting for these GEMM sizes on a many-core box (oversubscription): time a
+    ViT-block-sized matmul at a few thread counts and keep the best, so the baseline is the CPU's best case."""
+    import torch
+
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
+    a, b = torch.randn(1024, 1152), torch.randn(1152, 4304)
+    best, best_t = n, float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.mm(a, b)
+        t0 = time.time()
+        for _ in range(5):
+            torch.mm(a, b)
+        dt = time.time() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
 
 
 # --------------------------------------------------------------------------------------------- reference arm
@@ -311,7 +337,8 @@ def run_reference(a):
         sd = {k: v.float().cpu() for k, v in random_state_dict_device(cfg, 2024, "cuda:0").items()}
     else:
         sd = random_state_dict(cfg, 2024)
-    torch.set_num_threads(os.cpu_count() or 1)
+    threads = pick_cpu_threads()
+    torch.set_num_threads(threads)
     rs = np.random.RandomState(1000)
     n = a.steps + a.warmup
     pages = [Image.fromarray(rs.randint(0, 256, (a.page_px, a.page_px, 3), dtype=np.uint8)) for _ in range(n)]
@@ -328,7 +355,7 @@ def run_reference(a):
         "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[2]: full VisRAG-Ret encode of synthetic {a.page_px}x{a.page_px} pages", "model": a.model},
-        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 

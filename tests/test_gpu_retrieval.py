@@ -54,20 +54,27 @@ def test_ties_duplicates_and_short_corpus():
 
 def test_clustered_corpus_takes_the_exact_fallback_and_stays_correct():
     """More than 16 near-identical relevant docs inside one doc range defeat the per-range top-16 filter; the proof
-    step must notice (flag) and the fp32 fallback must still return the exact answer."""
+    step must notice (flag) and the fp32 fallback must still return the exact answer. The planted docs score within
+    ~1e-7 of each other, i.e. inside fp32 summation-order noise, so ids are compared through their oracle scores:
+    every returned doc must score (by the oracle) at least the oracle's k-th score minus 2e-6."""
     rs = np.random.RandomState(4)
     d = 128
     D = _unit(rs, 40000, d)
     Q = _unit(rs, 1500, d)
-    for qi in range(5):                               # 40 docs within ~1e-4 of query qi, all inside one doc tile
-        pert = Q[qi] + rs.randn(40, d).astype(np.float32) * 1e-5
+    for qi in range(5):                               # 40 docs within ~1e-3 of query qi, all inside one doc tile
+        pert = Q[qi] + rs.randn(40, d).astype(np.float32) * 1e-4
         D[5000 + 300 * qi: 5040 + 300 * qi] = pert / np.linalg.norm(pert, axis=1, keepdims=True)
     s, i, stats = _run(Q, D, 10)
     s_ref, i_ref = O.score_topk(Q, D, 10)
-    assert stats["flagged"] >= 1
-    assert np.array_equal(i, i_ref) and np.abs(s - s_ref).max() <= 2e-6
-    s2, i2, st2 = _run(Q[:50], D, 10, force_exact=True)
-    assert st2["path"] == "exact" and np.array_equal(i2, i_ref[:50])
+    assert stats["flagged"] >= 5
+    assert np.abs(s - s_ref).max() <= 2e-6 and (np.diff(s, axis=1) <= 0).all()
+    full = Q @ D.T
+    got_scores = np.take_along_axis(full, i, axis=1)
+    assert (got_scores >= s_ref[:, -1:] - 2e-6).all()
+    assert np.array_equal(i[5:], i_ref[5:])           # unperturbed queries: no near-ties, ids identical
+    assert all(len(set(r)) == 10 for r in i)
+    s2, i2, st2 = _run(Q[5:55], D, 10, force_exact=True)
+    assert st2["path"] == "exact" and np.array_equal(i2, i_ref[5:55])
 
 
 def test_large_problem_sets_match_torch_fp32():
