@@ -25,7 +25,11 @@ def test_elementwise_kernels():
 
 
 def test_attention_three_shapes():
-    assert CE.stage_attention()
+    assert CE.stage_attention()          # two-tile ping-pong kernel wherever max_q > 128
+
+
+def test_attention_three_shapes_single_tile_kernel():
+    assert CE.stage_attention(force_v1=True)
 
 
 def test_gemm_rejects_bad_arguments():

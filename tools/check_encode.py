@@ -88,10 +88,22 @@ def _attn_ref(q, k, v, scale, causal):
     return torch.softmax(s, -1) @ v.float()
 
 
-def stage_attention():
+def stage_attention(force_v1=False):
     import torch
-    from visrag_b200 import ops
+    from visrag_b200 import ops, _lib as L
 
+    L.lib().vr_attention_force_v1(1 if force_v1 else 0)
+    try:
+        return _stage_attention_body(torch, ops)
+    finally:
+        L.lib().vr_attention_force_v1(0)
+
+
+def stage_attention_v1():
+    return stage_attention(True)
+
+
+def _stage_attention_body(torch, ops):
     torch.manual_seed(1)
     ok = True
     dev = "cuda"
@@ -212,7 +224,8 @@ def stage_encode():
     return ok
 
 
-STAGES = {"elementwise": stage_elementwise, "attention": stage_attention, "vision": stage_vision, "encode": stage_encode}
+STAGES = {"elementwise": stage_elementwise, "attention": stage_attention, "attention_v1": stage_attention_v1,
+          "vision": stage_vision, "encode": stage_encode}
 
 if __name__ == "__main__":
     if len(sys.argv) == 2:

@@ -1,10 +1,11 @@
 #include <string.h>
 #include "common.h"
 #include "attention.cuh"
+#include "attention2.cuh"
 
 namespace vr {
 
-template <int HS, bool CAUSAL>
+template <int HS, bool CAUSAL, bool V2>
 static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     using Cfg = AttCfg<HS>;
     AttMaps maps;
@@ -26,19 +27,37 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.scale_log2 = p.scale * 1.4426950408889634f;
     a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
     a.ldo = p.ldo;
-    auto kern = attention_tcgen05_kernel<HS, CAUSAL>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
+    if constexpr (V2) {
+        // two 128-query tiles per CTA in ping-pong (sequences longer than one tile: the ViT)
+        using Cfg2 = Att2Cfg<HS>;
+        auto kern = attention2_tcgen05_kernel<HS, CAUSAL>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+            attr_set = true;
+        }
+        dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
+        kern<<<grid, ATT2_THREADS, Cfg2::SMEM_BYTES, stream>>>(maps, a);
+    } else {
+        auto kern = attention_tcgen05_kernel<HS, CAUSAL>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            attr_set = true;
+        }
+        dim3 grid((p.max_q + ATT_BM - 1) / ATT_BM, p.heads, p.batch);
+        kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a);
     }
-    dim3 grid((p.max_q + ATT_BM - 1) / ATT_BM, p.heads, p.batch);
-    kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
+static bool g_force_v1 = false;
+
 }  // namespace vr
+
+// test hook: force the single-tile kernel for every shape (lets the tests cover both kernels on the same inputs)
+extern "C" void vr_attention_force_v1(int32_t on) { vr::g_force_v1 = on != 0; }
 
 extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
     using namespace vr;
@@ -50,10 +69,15 @@ extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
     VR_REQUIRE(p->ldo % 8 == 0, "vr_attention: ldo must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const bool c = p->causal != 0;
+    const bool v2 = p->max_q > ATT_BM && !g_force_v1;  // more than one query tile per sequence
     switch (p->head_stride) {
-        case 64: return c ? launch_attention<64, true>(*p, s) : launch_attention<64, false>(*p, s);
-        case 80: return c ? launch_attention<80, true>(*p, s) : launch_attention<80, false>(*p, s);
-        case 128: return c ? launch_attention<128, true>(*p, s) : launch_attention<128, false>(*p, s);
+        case 64:
+            if (v2) return c ? launch_attention<64, true, true>(*p, s) : launch_attention<64, false, true>(*p, s);
+            return c ? launch_attention<64, true, false>(*p, s) : launch_attention<64, false, false>(*p, s);
+        case 80:
+            if (v2) return c ? launch_attention<80, true, true>(*p, s) : launch_attention<80, false, true>(*p, s);
+            return c ? launch_attention<80, true, false>(*p, s) : launch_attention<80, false, false>(*p, s);
+        case 128: return c ? launch_attention<128, true, false>(*p, s) : launch_attention<128, false, false>(*p, s);
         default: set_error("vr_attention: head_stride must be 64, 80 or 128 (got %d)", p->head_stride); return 2;
     }
 }

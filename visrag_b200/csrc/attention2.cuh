@@ -1,0 +1,359 @@
+// Attention v2: two 128-query tiles per CTA in ping-pong (the hot ViT shape: 1024 tokens, 16 heads x 72).
+//
+// The softmax of a 128x128 score tile needs 16384 exp2 on the SFU (MUFU: 16/clk/SM => 1024 cycles), more than the two
+// MMAs of the tile (640 cycles at head stride 80), so the design goal is to keep the SFUs busy all the time:
+//   warps 0-3  : softmax of query tile A (thread = one query row, S read from TMEM with tcgen05.ld)
+//   warps 4-7  : softmax of query tile B
+//   warp  8    : MMA issuer (one lane): S_x = Q_x K_j^T into TMEM, PV_x = P_x V_j into TMEM, x in {A, B}.
+//                S_A(j+1) is issued as soon as tile A's softmax(j) has consumed S_A(j), i.e. while tile B is still in
+//                its softmax: tensor core and SFU work overlap inside one CTA.
+//   warp  9    : TMA producer (one lane): Q_A, Q_B once; K_j / V_j through two-stage full/empty mbarrier rings.
+// The O accumulator lives in registers (O = O*alpha + PV, PV read back from TMEM); that update for iteration j is
+// deferred to iteration j+1 (after the row-max pass) so the P.V MMA latency is hidden behind SFU/ALU work.
+// Per-element ALU cost is cut with the sm_100 packed/3-input forms: FMNMX3 (max), FFMA2 (scale), FADD2 (sum), ex2.approx.
+//
+// TMEM (512 columns): S_A [0,128)  S_B [128,256)  PV_A [256,256+HS)  PV_B [384,384+HS).
+#pragma once
+#include "attention.cuh"
+
+namespace vr {
+
+constexpr int ATT2_THREADS = 320;
+
+template <int HS>
+struct Att2Cfg {
+    using C1 = AttCfg<HS>;
+    static_assert(HS == 64 || HS == 80, "v2 is built for head stride 64 / 80");
+    static constexpr int TILE = C1::TILE_BYTES;
+    static constexpr int OFF_QA = 0;
+    static constexpr int OFF_QB = TILE;
+    static constexpr int OFF_K = 2 * TILE;   // 2 stages
+    static constexpr int OFF_V = 4 * TILE;   // 2 stages
+    static constexpr int OFF_PA = 6 * TILE;
+    static constexpr int OFF_PB = 6 * TILE + 32768;
+    static constexpr int OFF_BAR = 6 * TILE + 65536;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float y;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+    return y;
+}
+// (a0,a1) * (b0,b1) + (c0,c1) in one FFMA2
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    unsigned long long A, B, Cc, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(Cc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(Cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+
+template <int HS, bool CAUSAL>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a) {
+    using Cfg = Att2Cfg<HS>;
+    using C1 = AttCfg<HS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* q_bar = bars + 0;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_bar = bars + 9;     // [2] per query tile
+    uint64_t* p_bar = bars + 11;    // [2]
+    uint64_t* o_bar = bars + 13;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qp = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int k_begin = a.cu_k[b];
+    const int len_k = a.cu_k[b + 1] - k_begin;
+    const int q_begin = a.cu_q ? a.cu_q[b] : 0;
+    const int len_q = a.cu_q ? a.cu_q[b + 1] - q_begin : a.max_q;
+    const int q0 = qp * 2 * ATT_BM;
+    if (q0 >= len_q || len_k <= 0) return;
+    const bool b_active = q0 + ATT_BM < len_q;
+    int nkt = (len_k + ATT_BN - 1) / ATT_BN;
+    if (CAUSAL) {
+        const int last_q = min(q0 + 2 * ATT_BM, len_q) - 1;
+        nkt = min(nkt, (last_q + (len_k - len_q)) / ATT_BN + 1);
+    }
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+            mbar_init(&s_bar[i], 1);
+            mbar_init(&p_bar[i], 128);
+            mbar_init(&o_bar[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 9) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            auto load_tile = [&](const CUtensorMap* m64, const CUtensorMap* m16, uint64_t* bar, uint8_t* dst, int col, int row) {
+#pragma unroll
+                for (int c = 0; c < C1::NCH; ++c) tma_load_2d(m64, bar, dst + c * 16384, col + c * 64, row);
+                if (C1::HAS16) tma_load_2d(m16, bar, dst + C1::NCH * 16384, col + C1::NCH * 64, row);
+            };
+            const int qcol = a.q_col0 + head * HS, kcol = a.k_col0 + head * HS, vcol = a.v_col0 + head * HS;
+            mbar_expect_tx(q_bar, Cfg::TILE * (b_active ? 2 : 1));
+            load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QA, qcol, q_begin + q0);
+            if (b_active) load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QB, qcol, q_begin + q0 + ATT_BM);
+            for (int j = 0; j < nkt; ++j) {
+                const int st = j & 1;
+                const uint32_t use_parity = (j >> 1) & 1;
+                mbar_wait(&k_empty[st], use_parity ^ 1);
+                mbar_expect_tx(&k_full[st], Cfg::TILE);
+                load_tile(&maps.k64, &maps.k16, &k_full[st], smem + Cfg::OFF_K + st * Cfg::TILE, kcol, k_begin + j * ATT_BN);
+                mbar_wait(&v_empty[st], use_parity ^ 1);
+                mbar_expect_tx(&v_full[st], Cfg::TILE);
+                load_tile(&maps.v64, &maps.v16, &v_full[st], smem + Cfg::OFF_V + st * Cfg::TILE, vcol, k_begin + j * ATT_BN);
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 1, 0, 0);
+            constexpr uint32_t idesc_pv64 = make_idesc_f16(128, 64, 1, 0, 1);
+            constexpr uint32_t idesc_pv16 = make_idesc_f16(128, 16, 1, 0, 1);
+            const uint32_t qa = smem_u32(smem + Cfg::OFF_QA), qb = smem_u32(smem + Cfg::OFF_QB);
+            const uint32_t kbase = smem_u32(smem + Cfg::OFF_K), vbase = smem_u32(smem + Cfg::OFF_V);
+            const uint32_t pa = smem_u32(smem + Cfg::OFF_PA), pb = smem_u32(smem + Cfg::OFF_PB);
+            auto issue_qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t d_tmem) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int c = 0; c < C1::NCH; ++c)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        umma_f16_ss(d_tmem, make_smem_desc(q_addr + c * 16384 + kk * 32, 16, 1024, kLayoutSW128),
+                                    make_smem_desc(k_addr + c * 16384 + kk * 32, 16, 1024, kLayoutSW128), idesc_qk, acc);
+                        acc = 1;
+                    }
+                if (C1::HAS16)
+                    umma_f16_ss(d_tmem, make_smem_desc(q_addr + C1::NCH * 16384, 16, 256, kLayoutSW32),
+                                make_smem_desc(k_addr + C1::NCH * 16384, 16, 256, kLayoutSW32), idesc_qk, acc);
+            };
+            auto issue_pv = [&](uint32_t p_addr, uint32_t v_addr, uint32_t d_tmem) {
+#pragma unroll
+                for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+                    const uint64_t pd = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, kLayoutSW128);
+#pragma unroll
+                    for (int c = 0; c < C1::NCH; ++c)
+                        umma_f16_ss(d_tmem + c * 64, pd, make_smem_desc(v_addr + c * 16384 + kk * 2048, 16, 1024, kLayoutSW128),
+                                    idesc_pv64, kk != 0);
+                    if (C1::HAS16)
+                        umma_f16_ss(d_tmem + C1::NCH * 64, pd,
+                                    make_smem_desc(v_addr + C1::NCH * 16384 + kk * 512, 16, 256, kLayoutSW32), idesc_pv16, kk != 0);
+                }
+            };
+            const uint32_t tS[2] = {tmem_base, tmem_base + 128}, tO[2] = {tmem_base + 256, tmem_base + 384};
+            mbar_wait(q_bar, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_qk(qa, kbase, tS[0]);
+            umma_commit(&s_bar[0]);
+            if (b_active) {
+                issue_qk(qb, kbase, tS[1]);
+                umma_commit(&s_bar[1]);
+            }
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < nkt; ++j) {
+                const int st = j & 1, nst = st ^ 1;
+                const uint32_t ph = j & 1, use_parity = (j >> 1) & 1, nuse_parity = ((j + 1) >> 1) & 1;
+                const bool more = j + 1 < nkt;
+                mbar_wait(&v_full[st], use_parity);
+                mbar_wait(&p_bar[0], ph);
+                tc_fence_after();
+                issue_pv(pa, vbase + st * Cfg::TILE, tO[0]);
+                umma_commit(&o_bar[0]);
+                if (more) {
+                    mbar_wait(&k_full[nst], nuse_parity);
+                    tc_fence_after();
+                    issue_qk(qa, kbase + nst * Cfg::TILE, tS[0]);
+                    umma_commit(&s_bar[0]);
+                }
+                if (b_active) {
+                    mbar_wait(&p_bar[1], ph);
+                    tc_fence_after();
+                    issue_pv(pb, vbase + st * Cfg::TILE, tO[1]);
+                    umma_commit(&o_bar[1]);
+                }
+                umma_commit(&v_empty[st]);
+                if (more) {
+                    if (b_active) {
+                        issue_qk(qb, kbase + nst * Cfg::TILE, tS[1]);
+                        umma_commit(&s_bar[1]);
+                    }
+                    umma_commit(&k_empty[nst]);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- softmax warpgroups
+        const int x = warp >> 2;  // 0 = tile A, 1 = tile B
+        if (x == 0 || b_active) {
+            const int r = threadIdx.x & 127;
+            const int q_idx = q0 + x * ATT_BM + r;
+            const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+            const uint32_t tmem_s = tmem_base + x * 128 + lane_off;
+            const uint32_t tmem_o = tmem_base + 256 + x * 128 + lane_off;
+            const int causal_shift = len_k - len_q;
+            const float sl2 = a.scale_log2;
+            float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+            float o[HS];
+#pragma unroll
+            for (int j = 0; j < HS; ++j) o[j] = 0.f;
+            uint8_t* p_row = smem + (x ? Cfg::OFF_PB : Cfg::OFF_PA) + (r >> 3) * 1024 + (r & 7) * 128;
+
+            auto o_update = [&](float alpha) {
+#pragma unroll
+                for (int c = 0; c < HS / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_o + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2)
+                        fma2(o[c * 32 + j], o[c * 32 + j + 1], o[c * 32 + j], o[c * 32 + j + 1], alpha, alpha,
+                             __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                }
+                if (HS % 32 == 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(tmem_o + (HS / 32) * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2)
+                        fma2(o[(HS / 32) * 32 + j], o[(HS / 32) * 32 + j + 1], o[(HS / 32) * 32 + j], o[(HS / 32) * 32 + j + 1],
+                             alpha, alpha, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                }
+            };
+
+            for (int kt = 0; kt < nkt; ++kt) {
+                const uint32_t ph = kt & 1;
+                const int key0 = kt * ATT_BN;
+                int limit = len_k - key0;
+                if (CAUSAL) limit = min(limit, q_idx + causal_shift - key0 + 1);
+                const bool full = limit >= ATT_BN;
+                mbar_wait(&s_bar[x], ph);
+                tc_fence_after();
+                // pass 1: row max
+                float m_tile = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_s + c * 32, v);
+                    tmem_ld_wait();
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) m_tile = max3(m_tile, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j < limit) m_tile = fmaxf(m_tile, __uint_as_float(v[j]));
+                    }
+                }
+                const float m_new = fmaxf(m_run, m_tile);
+                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                const float alpha = ex2_approx((m_run - m_use) * sl2);
+                const float neg_ms = -m_use * sl2;
+                // deferred O update of the previous key block (its P.V MMA ran behind pass 1); also frees P smem
+                if (kt > 0) {
+                    mbar_wait(&o_bar[x], ph ^ 1);
+                    tc_fence_after();
+                    o_update(alpha_prev);
+                }
+                // pass 2: p = 2^(s*scale*log2e - m*scale*log2e), bf16 into swizzled smem
+                float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_s + c * 32, v);
+                    tmem_ld_wait();
+                    float p[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float t0, t1;
+                        fma2(t0, t1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), sl2, sl2, neg_ms, neg_ms);
+                        p[j] = ex2_approx(t0);
+                        p[j + 1] = ex2_approx(t1);
+                    }
+                    if (!full) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j >= limit) p[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        l0 += p[j];
+                        l1 += p[j + 1];
+                    }
+                    uint8_t* dst = p_row + (c >> 1) * 16384;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(p[i * 8 + 0], p[i * 8 + 1]);
+                        pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
+                        pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
+                        pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
+                        const int piece = (c & 1) * 4 + i;
+                        *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
+                    }
+                }
+                l_run = l_run * alpha + (l0 + l1);
+                m_run = m_new;
+                alpha_prev = alpha;
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&p_bar[x]);
+            }
+            mbar_wait(&o_bar[x], (nkt - 1) & 1);
+            tc_fence_after();
+            // the last block's alpha was already folded into l_run; O still needs it
+            o_update(alpha_prev);
+            if (q_idx < len_q) {
+                const float inv = 1.0f / l_run;
+                const long long row = a.cu_q ? (long long)(q_begin + q_idx) : (long long)b * a.max_q + q_idx;
+                __nv_bfloat16* dst = a.out + row * a.ldo + head * a.head_dim;
+#pragma unroll
+                for (int j8 = 0; j8 < HS / 8; ++j8) {
+                    if (j8 * 8 < a.head_dim) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(o[j8 * 8 + 0] * inv, o[j8 * 8 + 1] * inv);
+                        pk.y = pack_bf16x2(o[j8 * 8 + 2] * inv, o[j8 * 8 + 3] * inv);
+                        pk.z = pack_bf16x2(o[j8 * 8 + 4] * inv, o[j8 * 8 + 5] * inv);
+                        pk.w = pack_bf16x2(o[j8 * 8 + 6] * inv, o[j8 * 8 + 7] * inv);
+                        *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace vr

@@ -29,7 +29,8 @@ struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
 };
 
@@ -42,85 +43,143 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------
-// Epilogue bodies. Each thread owns output row `row`; `v` holds 32 consecutive accumulator
-// columns starting at global column `col0`.
+// Epilogue. tcgen05.ld hands every thread ONE output row (32 consecutive columns per chunk), which is the wrong shape
+// for global memory: a warp-wide 16-byte access would touch 32 different rows. Each epilogue warp therefore owns a 4 KB
+// shared-memory transpose buffer: values go thread-row -> smem -> row-contiguous 16-byte global accesses (8 lanes cover
+// one 128-byte row segment), and the fp32 residual comes in the opposite way. The buffer is XOR-swizzled in 16-byte
+// units so both directions are bank-conflict free.
+//   "wide" tile : 32 rows x 128 B (32 fp32, or 64 bf16)   unit u of row r lives at r*128 + ((u ^ (r&7)) << 4)
+//   "half" tile : 32 rows x  64 B (32 bf16)               unit u of row r lives at r*64  + ((u ^ ((r>>1)&3)) << 4)
 // ---------------------------------------------------------------------------------------
-template <bool OUT_F32, bool GELU>
-__device__ __forceinline__ void epi_linear(const GemmArgs& g, int row, int col0, float (&v)[32]) {
-    const vr_gemm_epilogue& e = g.epi;
-    if (row >= g.M) return;
-    const int N = g.N;
+__device__ __forceinline__ uint32_t wide_off(int r, int u) { return r * 128 + ((u ^ (r & 7)) << 4); }
+__device__ __forceinline__ uint32_t half_off(int r, int u) { return r * 64 + ((u ^ ((r >> 1) & 3)) << 4); }
+
+// this thread's row (lane) -> smem, 8 x 16 B
+__device__ __forceinline__ void stage_put_wide(uint8_t* st, int lane, const uint32_t (&w)[32]) {
 #pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-        const int c = col0 + j8 * 8;
-        if (c >= N) break;  // N % 8 == 0: a group of 8 is entirely in or out
-        float x[8];
+    for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<uint4*>(st + wide_off(lane, u)) = make_uint4(w[u * 4], w[u * 4 + 1], w[u * 4 + 2], w[u * 4 + 3]);
+}
+__device__ __forceinline__ void stage_get_wide(const uint8_t* st, int lane, uint32_t (&w)[32]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = v[j8 * 8 + j];
-        if (e.bias) {
-            const float4 b0 = *reinterpret_cast<const float4*>(e.bias + c);
-            const float4 b1 = *reinterpret_cast<const float4*>(e.bias + c + 4);
-            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-        }
-        if (GELU) {
+    for (int u = 0; u < 8; ++u) {
+        const uint4 q = *reinterpret_cast<const uint4*>(st + wide_off(lane, u));
+        w[u * 4] = q.x; w[u * 4 + 1] = q.y; w[u * 4 + 2] = q.z; w[u * 4 + 3] = q.w;
+    }
+}
+// smem <-> global, row-contiguous: lane handles 16 B of row (i*4 + lane/8); `elems16` = elements per 16 bytes
+template <typename T>
+__device__ __forceinline__ void stage_store_wide(const uint8_t* st, int lane, T* gbase, long long ld, int row0, int rows_valid,
+                                                 int col0, int cols_valid) {
+    constexpr int E = 16 / sizeof(T);
+    const int u = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
-        }
-        if (e.scale != 1.0f) {
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        if (r < rows_valid && u * E < cols_valid)
+            *reinterpret_cast<uint4*>(gbase + static_cast<long long>(row0 + r) * ld + col0 + u * E) =
+                *reinterpret_cast<const uint4*>(st + wide_off(r, u));
+    }
+}
+__device__ __forceinline__ void stage_load_wide_f32(uint8_t* st, int lane, const float* gbase, long long ld, int row0,
+                                                    int rows_valid, int col0, int cols_valid) {
+    const int u = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] *= e.scale;
-        }
-        if (e.rowadd) {
-            const float* p = e.rowadd + static_cast<int64_t>(row % e.rowadd_period) * N + c;
-            const float4 a0 = *reinterpret_cast<const float4*>(p);
-            const float4 a1 = *reinterpret_cast<const float4*>(p + 4);
-            x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
-            x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
-        }
-        if (e.resid) {
-            const float* p = e.resid + static_cast<int64_t>(row) * e.ldo + c;
-            const float4 a0 = *reinterpret_cast<const float4*>(p);
-            const float4 a1 = *reinterpret_cast<const float4*>(p + 4);
-            x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
-            x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
-        }
-        if (OUT_F32) {
-            float* o = reinterpret_cast<float*>(e.out) + static_cast<int64_t>(row) * e.ldo + c;
-            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-        } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + static_cast<int64_t>(row) * e.ldo + c;
-            uint4 pk;
-            pk.x = pack_bf16x2(x[0], x[1]);
-            pk.y = pack_bf16x2(x[2], x[3]);
-            pk.z = pack_bf16x2(x[4], x[5]);
-            pk.w = pack_bf16x2(x[6], x[7]);
-            *reinterpret_cast<uint4*>(o) = pk;
-        }
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (r < rows_valid && u * 4 < cols_valid)
+            q = *reinterpret_cast<const uint4*>(gbase + static_cast<long long>(row0 + r) * ld + col0 + u * 4);
+        *reinterpret_cast<uint4*>(st + wide_off(r, u)) = q;
+    }
+}
+__device__ __forceinline__ void stage_put_half(uint8_t* st, int lane, const uint32_t (&w)[16]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(st + half_off(lane, u)) = make_uint4(w[u * 4], w[u * 4 + 1], w[u * 4 + 2], w[u * 4 + 3]);
+}
+__device__ __forceinline__ void stage_store_half(const uint8_t* st, int lane, __nv_bfloat16* gbase, long long ld, int row0,
+                                                 int rows_valid, int col0, int cols_valid) {
+    const int u = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        if (r < rows_valid && u * 8 < cols_valid)
+            *reinterpret_cast<uint4*>(gbase + static_cast<long long>(row0 + r) * ld + col0 + u * 8) =
+                *reinterpret_cast<const uint4*>(st + half_off(r, u));
     }
 }
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* o, const float (&x)[32]) {
+// LINEAR: out = [resid +] scale * gelu?(acc + bias) [+ rowadd[row % period]]   (one 32-column chunk of one warp)
+template <bool OUT_F32, bool GELU>
+__device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&x)[32]) {
+    const vr_gemm_epilogue& e = g.epi;
+    const int rows_valid = g.M - row0;          // may exceed 32
+    const int cols_valid = g.N - col0;          // may exceed 32; N % 8 == 0
+    if (rows_valid <= 0 || cols_valid <= 0) return;  // warp-uniform
+    if (e.bias) {
 #pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-        uint4 pk;
-        pk.x = pack_bf16x2(x[j8 * 8 + 0], x[j8 * 8 + 1]);
-        pk.y = pack_bf16x2(x[j8 * 8 + 2], x[j8 * 8 + 3]);
-        pk.z = pack_bf16x2(x[j8 * 8 + 4], x[j8 * 8 + 5]);
-        pk.w = pack_bf16x2(x[j8 * 8 + 6], x[j8 * 8 + 7]);
-        *reinterpret_cast<uint4*>(o + j8 * 8) = pk;
+        for (int j4 = 0; j4 < 8; ++j4) {
+            if (j4 * 4 < cols_valid) {
+                const float4 b = *reinterpret_cast<const float4*>(e.bias + col0 + j4 * 4);
+                x[j4 * 4] += b.x; x[j4 * 4 + 1] += b.y; x[j4 * 4 + 2] += b.z; x[j4 * 4 + 3] += b.w;
+            }
+        }
     }
+    if (GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (e.scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] *= e.scale;
+    }
+    if (e.rowadd && lane < rows_valid) {
+        const float* p = e.rowadd + static_cast<long long>((row0 + lane) % e.rowadd_period) * g.N + col0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            if (j4 * 4 < cols_valid) {
+                const float4 a4 = *reinterpret_cast<const float4*>(p + j4 * 4);
+                x[j4 * 4] += a4.x; x[j4 * 4 + 1] += a4.y; x[j4 * 4 + 2] += a4.z; x[j4 * 4 + 3] += a4.w;
+            }
+        }
+    }
+    if (e.resid) {
+        stage_load_wide_f32(st, lane, e.resid, e.ldo, row0, rows_valid, col0, cols_valid);
+        __syncwarp();
+        uint32_t w[32];
+        stage_get_wide(st, lane, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(w[j]);
+        __syncwarp();
+    }
+    if (OUT_F32) {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(x[j]);
+        stage_put_wide(st, lane, w);
+        __syncwarp();
+        stage_store_wide<float>(st, lane, reinterpret_cast<float*>(e.out), e.ldo, row0, rows_valid, col0, cols_valid);
+    } else {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+        stage_put_half(st, lane, w);
+        __syncwarp();
+        stage_store_half(st, lane, reinterpret_cast<__nv_bfloat16*>(e.out), e.ldo, row0, rows_valid, col0, cols_valid);
+    }
+    __syncwarp();
 }
 
 // RoPE (modeling_minicpm.py:259-290): a head is 64 columns [lo(32) | hi(32)];
-//   lo' = lo*cos - hi*sin ; hi' = hi*cos + lo*sin   with cos/sin[pos, 0..31].
-__device__ __forceinline__ void epi_rope(const GemmArgs& g, int row, int col0, float (&lo)[32], float (&hi)[32]) {
+//   lo' = lo*cos - hi*sin ; hi' = hi*cos + lo*sin   with cos/sin[pos, 0..31].  Writes 64 bf16 columns.
+__device__ __forceinline__ void epi_rope(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&lo)[32],
+                                         float (&hi)[32]) {
     const vr_gemm_epilogue& e = g.epi;
-    if (row >= g.M) return;
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + static_cast<int64_t>(row) * e.ldo + col0;
-    if (col0 < e.rope_cols) {
-        const int pos = e.positions[row];
+    const int rows_valid = g.M - row0;
+    if (rows_valid <= 0) return;
+    if (col0 < e.rope_cols && lane < rows_valid) {
+        const int pos = e.positions[row0 + lane];
         const float* cs = e.rope_cos + static_cast<int64_t>(pos) * 32;
         const float* sn = e.rope_sin + static_cast<int64_t>(pos) * 32;
 #pragma unroll
@@ -137,18 +196,31 @@ __device__ __forceinline__ void epi_rope(const GemmArgs& g, int row, int col0, f
             }
         }
     }
-    store_bf16x32(o, lo);
-    store_bf16x32(o + 32, hi);
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        w[j] = pack_bf16x2(lo[2 * j], lo[2 * j + 1]);
+        w[16 + j] = pack_bf16x2(hi[2 * j], hi[2 * j + 1]);
+    }
+    stage_put_wide(st, lane, w);
+    __syncwarp();
+    stage_store_wide<__nv_bfloat16>(st, lane, reinterpret_cast<__nv_bfloat16*>(e.out), e.ldo, row0, rows_valid, col0, 64);
+    __syncwarp();
 }
 
-// SwiGLU (modeling_minicpm.py:333): accumulator columns [gate(32) | up(32)] -> 32 outputs.
-__device__ __forceinline__ void epi_swiglu(const GemmArgs& g, int row, int col0, float (&gt)[32], float (&up)[32]) {
+// SwiGLU (modeling_minicpm.py:333): accumulator columns [gate(32) | up(32)] -> 32 bf16 outputs at column col0/2.
+__device__ __forceinline__ void epi_swiglu(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&gt)[32],
+                                           float (&up)[32]) {
     const vr_gemm_epilogue& e = g.epi;
-    if (row >= g.M) return;
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + static_cast<int64_t>(row) * e.ldo + (col0 >> 1);
+    const int rows_valid = g.M - row0;
+    if (rows_valid <= 0) return;
+    uint32_t w[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) gt[j] = silu(gt[j]) * up[j];
-    store_bf16x32(o, gt);
+    for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(silu(gt[2 * j]) * up[2 * j], silu(gt[2 * j + 1]) * up[2 * j + 1]);
+    stage_put_half(st, lane, w);
+    __syncwarp();
+    stage_store_half(st, lane, reinterpret_cast<__nv_bfloat16*>(e.out), e.ldo, row0, rows_valid, col0 >> 1, 32);
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -163,7 +235,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* smem_stage = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + GEMM_EPI_WARPS * Cfg::EPI_STAGE_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -266,7 +339,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (t / tiles_n) * GEMM_BM;
             const int n0 = (t % tiles_n) * BN;
-            const int row = m0 + quarter * 32 + lane;
+            const int row0 = m0 + quarter * 32;  // first of this warp's 32 rows
+            uint8_t* st = smem_stage + ew * Cfg::EPI_STAGE_BYTES;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
@@ -285,7 +359,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epi_linear<OUT_F32, GELU>(g, row, n0 + half * COLS_PER_WARP + c * 32, v);
+                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
                 }
             } else {
 #pragma unroll 1
@@ -307,8 +381,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     const int col0 = n0 + half * COLS_PER_WARP + c * 64;
                     if (col0 < g.N) {
-                        if (MODE == VR_EPI_ROPE) epi_rope(g, row, col0, a, b);
-                        else epi_swiglu(g, row, col0, a, b);
+                        if (MODE == VR_EPI_ROPE) epi_rope(g, st, lane, row0, col0, a, b);
+                        else epi_swiglu(g, st, lane, row0, col0, a, b);
                     }
                 }
             }
