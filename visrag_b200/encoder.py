@@ -228,6 +228,20 @@ class VisRAGEngine:
         stage.copy_(t)
         return stage.to(self.device, non_blocking=True)
 
+    def _stage_slices(self, slices, key) -> torch.Tensor:
+        """List of S uint8 [h,w,3] arrays -> device [S,h,w,3], copied slice by slice into the pinned staging buffer."""
+        h, w, c = slices[0].shape
+        n = len(slices) * h * w * c
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(n, dtype=torch.uint8).pin_memory()
+            self._pinned[key] = buf
+        stage = buf[:n].view(len(slices), h, w, c)
+        dst = stage.numpy()
+        for j, a in enumerate(slices):
+            dst[j] = a
+        return stage.to(self.device, non_blocking=True)
+
     def upload(self, pb: PreparedBatch):
         """Host -> device copies of one prepared batch: pinned staging, async on the current stream. The staging
         buffers are reused, so the previous upload's copies are waited for first (they finished long ago)."""
@@ -235,7 +249,7 @@ class VisRAGEngine:
             self._pinned, self._upload_done = {}, None
         if self._upload_done is not None:
             self._upload_done.synchronize()
-        groups = {k: self._stage(v, ("px", k)) for k, v in pb.groups.items()}
+        groups = {k: self._stage_slices(v, ("px", k)) for k, v in pb.groups.items()}
         out = groups, self._stage(pb.token_src, "src"), self._stage(pb.positions, "pos"), self._stage(pb.cu_seqlens, "cu")
         self._upload_done = torch.cuda.Event()
         self._upload_done.record()

@@ -129,9 +129,12 @@ class PreparedBatch:
     cu_seqlens: np.ndarray               # [B+1] int32
     positions: np.ndarray                # [T] int32, position inside the sequence
     token_src: np.ndarray                # [T] int32: >=0 row of the vision buffer; <0 -> -(token_id+1)
-    groups: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)   # (h,w) -> uint8 [S,h,w,3]
+    groups: Dict[Tuple[int, int], List[np.ndarray]] = field(default_factory=dict)   # (h,w) -> S uint8 [h,w,3] slices
     group_row0: Dict[Tuple[int, int], int] = field(default_factory=dict)      # (h,w) -> first slice index
     n_slices: int = 0
+
+    def pixel_bytes(self) -> int:
+        return sum(a.nbytes for lst in self.groups.values() for a in lst)
 
 
 def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAGConfig,
@@ -171,7 +174,7 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
         slot.append(cur)
     groups, row0, base = {}, {}, 0
     for key, lst in order.items():
-        groups[key] = np.stack(lst, axis=0)
+        groups[key] = lst  # stacked straight into pinned staging memory by the engine (no intermediate copy)
         row0[key] = base
         base += len(lst)
 
