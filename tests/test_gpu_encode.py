@@ -112,3 +112,55 @@ def test_batch_composition_does_not_change_results():
     mixed = eng.encode(["", "", "query text", ""], [pages[0], pages[1], None, pages[2]], tok)
     assert torch.equal(alone[0], mixed[1])
     assert eng.encode([], [], tok).shape == (0, cfg.hidden)
+
+
+def test_config1_pipeline_encode_shards_retrieve_trec_metrics(tmp_path):
+    """BASELINE configs[0]: 4 queries x 32 synthetic 224x224 pages through the reference-signature pipeline
+    (encode loop -> pickle shards -> retrieve -> TREC run -> metrics) vs the oracle's embeddings + numpy cosine top-5."""
+    from types import SimpleNamespace
+
+    from oracle import restated as O
+    from visrag_b200 import inference as I
+    from visrag_b200 import retriever as R
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.synth import synth_queries
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    cfg = VisRAGConfig.tiny()
+    sd = random_state_dict(cfg, 2025)
+    tok = StubTokenizer(cfg.vocab)
+    pages = synth_pages([(224, 224)] * 32, 1235)
+    queries = synth_queries(4, 1235)
+    model = _engine_model(cfg, sd)
+    args = SimpleNamespace(output_dir=str(tmp_path), per_device_eval_batch_size=5, max_inmem_docs=12, world_size=1,
+                           process_index=0, device="cuda:0")
+    corpus = [{"id": f"d{i}", "text": "", "image": im} for i, im in enumerate(pages)]
+    qset = [{"id": f"q{i}", "text": t, "image": None} for i, t in enumerate(queries)]
+    kw = {"tokenizer": tok, "max_inp_length": 2048}
+    I.distributed_parallel_embedding_inference(corpus, model, args, "corpus", True, kw)
+    I.distributed_parallel_embedding_inference(qset, model, args, "query", False, kw)
+    import glob
+    import os
+
+    shards = sorted(glob.glob(os.path.join(str(tmp_path), "embeddings.corpus.rank.0.*")))
+    assert [os.path.basename(s).split(".")[-1] for s in shards] == ["0-15", "15-30", "30-32"]  # flush rule of inference.py:112
+    emb, ids = R.load_shard(shards[0])
+    assert emb.dtype == np.float32 and emb.shape == (15, cfg.hidden) and ids[0] == "d0"
+    run = R.distributed_parallel_retrieve(args, 5)
+    I.save_as_trec(run, os.path.join(str(tmp_path), "test.0.trec"))
+    run2 = I.load_from_trec(os.path.join(str(tmp_path), "test.0.trec"))
+    p_ref = O.encode(sd, cfg, tok, [""] * 32, pages)
+    q_ref = O.encode(sd, cfg, tok, queries, [None] * 4)
+    s_ref, top_ref = O.score_topk(q_ref, p_ref, 5)
+    full_ref = q_ref @ p_ref.T
+    qrels = {}
+    for qi in range(4):
+        ranked = sorted(run2[f"q{qi}"].items(), key=lambda kv: -kv[1])[:5]
+        got = [int(d[1:]) for d, _ in ranked]
+        # same top-5 up to near-ties: noise pages of one size embed close together, so allow the bf16 score noise (5e-3)
+        assert (full_ref[qi, got] >= s_ref[qi, -1] - 5e-3).all() and len(set(got)) == 5
+        assert abs(ranked[0][1] - s_ref[qi, 0]) <= 5e-3
+        qrels[f"q{qi}"] = {ranked[0][0]: 1}
+    m = I.save_results(str(tmp_path), qrels, run2)
+    assert m["recall_10"] == 1.0 and m["mrr_10"] == 1.0 and m["ndcg_cut_10"] == 1.0

@@ -324,33 +324,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, AB_FMT, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // The WHOLE warp runs this loop with warp-uniform control flow (so stage / phase / descriptors live in uniform
+        // registers); one elected lane issues the tcgen05 instructions. A per-thread `if (lane == 0)` around the loop
+        // makes the compiler wrap every UTCHMMA in a uniformisation loop and the single issuing thread becomes the
+        // bottleneck (measured: 115 SASS instructions per k-block, tensor pipe 71 % busy).
+        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN, AB_FMT, 0, 0);
+        // descriptor = constant high word | (address >> 4); K-major SW128: LBO 16 B (unused), SBO 1024 B
+        const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128);
+        const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
-#pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        // K-major SW128: 8-row groups are 1024 B apart; +32 B per 16-element K step
-                        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, kLayoutSW128);
-                        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, kLayoutSW128);
-                        umma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                if (elect_one()) {
+                    const uint64_t ad = desc_hi | static_cast<uint64_t>(a_lo0 + stage * (Cfg::A_BYTES >> 4));
+                    const uint64_t bd = desc_hi | static_cast<uint64_t>(b_lo0 + stage * (Cfg::B_BYTES >> 4));
+                    // +32 B (= +2 in the >>4 address field) per 16-element K step inside the 128 B swizzle row
+                    umma_f16_ss(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+                    umma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                    umma_f16_ss(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                    umma_f16_ss(d_tmem, ad + 6, bd + 6, idesc, 1u);
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {

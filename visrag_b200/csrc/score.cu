@@ -110,29 +110,33 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, SC_BN, 0 /*fp16*/, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int t = t_begin; t < t_end; ++t, ++it) {
-                const int acc = it & 1;
-                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        // whole warp, warp-uniform control flow, one elected lane issues (see gemm.cuh)
+        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, SC_BN, 0 /*fp16*/, 0, 0);
+        const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128);
+        const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int t = t_begin; t < t_end; ++t, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * SC_BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * SC_BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
-#pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_f16_ss(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024, kLayoutSW128),
-                                    make_smem_desc(b_addr + k * 32, 16, 1024, kLayoutSW128), idesc, (kb | k) != 0);
+                if (elect_one()) {
+                    const uint64_t ad = desc_hi | static_cast<uint64_t>(a_lo0 + stage * (Cfg::A_BYTES >> 4));
+                    const uint64_t bd = desc_hi | static_cast<uint64_t>(b_lo0 + stage * (Cfg::B_BYTES >> 4));
+                    umma_f16_ss(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+                    umma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                    umma_f16_ss(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                    umma_f16_ss(d_tmem, ad + 6, bd + 6, idesc, 1u);
                     umma_commit(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
