@@ -158,6 +158,38 @@ def _stage_attention_body(torch, ops):
     return ok
 
 
+def stage_attention_perf():
+    """ViT attention at bench shape (128 slices x 16 heads x 1024 tokens x 72) timed alone: TFLOP/s of 4*N^2*D."""
+    import torch
+    from visrag_b200 import ops, _lib as L
+
+    S, N, nh, hd, hs = 128, 1024, 16, 72, 80
+    qkv = torch.zeros(S * N, 3, nh, hs, device="cuda")
+    qkv[..., :hd] = torch.randn(S * N, 3, nh, hd, device="cuda")
+    qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
+    cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device="cuda")
+    out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device="cuda")
+    for force in (0, 1):
+        L.lib().vr_attention_force_v1(force)
+
+        def run():
+            ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
+                          batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"attention {'v1' if force else 'v2'}: {ms:.3f} ms  {4.0 * N * N * nh * hd * S / ms / 1e9:.1f} TFLOP/s (useful)", flush=True)
+    L.lib().vr_attention_force_v1(0)
+    return True
+
+
 def _tiny():
     from tests.helpers import load_case
     from visrag_b200.weights import random_state_dict
@@ -225,7 +257,7 @@ def stage_encode():
 
 
 STAGES = {"elementwise": stage_elementwise, "attention": stage_attention, "attention_v1": stage_attention_v1,
-          "vision": stage_vision, "encode": stage_encode}
+          "attention_perf": stage_attention_perf, "vision": stage_vision, "encode": stage_encode}
 
 if __name__ == "__main__":
     if len(sys.argv) == 2:

@@ -18,7 +18,7 @@
 
 namespace vr {
 
-constexpr int ATT2_THREADS = 320;
+constexpr int ATT2_THREADS = 384;  // 2 softmax warpgroups + 1 control warpgroup (issuer, producer, 2 idle warps)
 
 template <int HS>
 struct Att2Cfg {
@@ -107,7 +107,11 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register rebalancing (per-SMSP register files: 12 warps x 168 regs at launch): the control warpgroup gives
+    // registers away, the softmax warpgroups grow so that the O row (80 fp32) and two S chunks fit without spills.
+    // Each setmaxnreg sits at the top of its own role branch (the allocator applies the limit to the code it dominates).
     if (warp == 9) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
             auto load_tile = [&](const CUtensorMap* m64, const CUtensorMap* m16, uint64_t* bar, uint8_t* dst, int col, int row) {
@@ -131,84 +135,96 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             }
         }
     } else if (warp == 8) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 1, 0, 0);
-            constexpr uint32_t idesc_pv64 = make_idesc_f16(128, 64, 1, 0, 1);
-            constexpr uint32_t idesc_pv16 = make_idesc_f16(128, 16, 1, 0, 1);
-            const uint32_t qa = smem_u32(smem + Cfg::OFF_QA), qb = smem_u32(smem + Cfg::OFF_QB);
-            const uint32_t kbase = smem_u32(smem + Cfg::OFF_K), vbase = smem_u32(smem + Cfg::OFF_V);
-            const uint32_t pa = smem_u32(smem + Cfg::OFF_PA), pb = smem_u32(smem + Cfg::OFF_PB);
-            auto issue_qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t d_tmem) {
-                uint32_t acc = 0;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        // ------------------------------------------------------------ MMA issuer: the whole warp runs the (warp-uniform)
+        // control flow, one elected lane issues each block of tcgen05.mma (keeps descriptors in uniform registers)
+        constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 1, 0, 0);
+        constexpr uint32_t idesc_pv64 = make_idesc_f16(128, 64, 1, 0, 1);
+        constexpr uint32_t idesc_pv16 = make_idesc_f16(128, 16, 1, 0, 1);
+        const uint64_t hi128 = make_smem_desc(0, 16, 1024, kLayoutSW128);
+        const uint64_t hi32 = make_smem_desc(0, 16, 256, kLayoutSW32);
+        const uint32_t qa = smem_u32(smem + Cfg::OFF_QA) >> 4, qb = smem_u32(smem + Cfg::OFF_QB) >> 4;
+        const uint32_t kbase = smem_u32(smem + Cfg::OFF_K) >> 4, vbase = smem_u32(smem + Cfg::OFF_V) >> 4;
+        const uint32_t pa = smem_u32(smem + Cfg::OFF_PA) >> 4, pb = smem_u32(smem + Cfg::OFF_PB) >> 4;
+        constexpr uint32_t TILE16 = Cfg::TILE >> 4;
+        // all addresses below are in 16-byte units (the descriptor's address field)
+        auto issue_qk = [&](uint32_t q16, uint32_t k16, uint32_t d_tmem) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < C1::NCH; ++c)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    umma_f16_ss(d_tmem, hi128 | (q16 + c * 1024 + kk * 2), hi128 | (k16 + c * 1024 + kk * 2), idesc_qk, acc);
+                    acc = 1;
+                }
+            if (C1::HAS16) umma_f16_ss(d_tmem, hi32 | (q16 + C1::NCH * 1024), hi32 | (k16 + C1::NCH * 1024), idesc_qk, acc);
+        };
+        auto issue_pv = [&](uint32_t p16, uint32_t v16, uint32_t d_tmem) {
+#pragma unroll
+            for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+                const uint64_t pd = hi128 | (p16 + (kk >> 2) * 1024 + (kk & 3) * 2);
 #pragma unroll
                 for (int c = 0; c < C1::NCH; ++c)
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        umma_f16_ss(d_tmem, make_smem_desc(q_addr + c * 16384 + kk * 32, 16, 1024, kLayoutSW128),
-                                    make_smem_desc(k_addr + c * 16384 + kk * 32, 16, 1024, kLayoutSW128), idesc_qk, acc);
-                        acc = 1;
-                    }
+                    umma_f16_ss(d_tmem + c * 64, pd, hi128 | (v16 + c * 1024 + kk * 128), idesc_pv64, kk != 0);
                 if (C1::HAS16)
-                    umma_f16_ss(d_tmem, make_smem_desc(q_addr + C1::NCH * 16384, 16, 256, kLayoutSW32),
-                                make_smem_desc(k_addr + C1::NCH * 16384, 16, 256, kLayoutSW32), idesc_qk, acc);
-            };
-            auto issue_pv = [&](uint32_t p_addr, uint32_t v_addr, uint32_t d_tmem) {
-#pragma unroll
-                for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-                    const uint64_t pd = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, kLayoutSW128);
-#pragma unroll
-                    for (int c = 0; c < C1::NCH; ++c)
-                        umma_f16_ss(d_tmem + c * 64, pd, make_smem_desc(v_addr + c * 16384 + kk * 2048, 16, 1024, kLayoutSW128),
-                                    idesc_pv64, kk != 0);
-                    if (C1::HAS16)
-                        umma_f16_ss(d_tmem + C1::NCH * 64, pd,
-                                    make_smem_desc(v_addr + C1::NCH * 16384 + kk * 512, 16, 256, kLayoutSW32), idesc_pv16, kk != 0);
-                }
-            };
-            const uint32_t tS[2] = {tmem_base, tmem_base + 128}, tO[2] = {tmem_base + 256, tmem_base + 384};
-            mbar_wait(q_bar, 0);
-            mbar_wait(&k_full[0], 0);
-            tc_fence_after();
-            issue_qk(qa, kbase, tS[0]);
+                    umma_f16_ss(d_tmem + C1::NCH * 64, pd, hi32 | (v16 + C1::NCH * 1024 + kk * 32), idesc_pv16, kk != 0);
+            }
+        };
+        const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 384;
+        mbar_wait(q_bar, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        if (elect_one()) {
+            issue_qk(qa, kbase, tS0);
             umma_commit(&s_bar[0]);
             if (b_active) {
-                issue_qk(qb, kbase, tS[1]);
+                issue_qk(qb, kbase, tS1);
                 umma_commit(&s_bar[1]);
             }
             umma_commit(&k_empty[0]);
-            for (int j = 0; j < nkt; ++j) {
-                const int st = j & 1, nst = st ^ 1;
-                const uint32_t ph = j & 1, use_parity = (j >> 1) & 1, nuse_parity = ((j + 1) >> 1) & 1;
-                const bool more = j + 1 < nkt;
-                mbar_wait(&v_full[st], use_parity);
-                mbar_wait(&p_bar[0], ph);
-                tc_fence_after();
-                issue_pv(pa, vbase + st * Cfg::TILE, tO[0]);
+        }
+        __syncwarp();
+        for (int j = 0; j < nkt; ++j) {
+            const int st = j & 1, nst = st ^ 1;
+            const uint32_t ph = j & 1, use_parity = (j >> 1) & 1, nuse_parity = ((j + 1) >> 1) & 1;
+            const bool more = j + 1 < nkt;
+            mbar_wait(&v_full[st], use_parity);
+            mbar_wait(&p_bar[0], ph);
+            if (more) mbar_wait(&k_full[nst], nuse_parity);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_pv(pa, vbase + st * TILE16, tO0);
                 umma_commit(&o_bar[0]);
                 if (more) {
-                    mbar_wait(&k_full[nst], nuse_parity);
-                    tc_fence_after();
-                    issue_qk(qa, kbase + nst * Cfg::TILE, tS[0]);
+                    issue_qk(qa, kbase + nst * TILE16, tS0);
                     umma_commit(&s_bar[0]);
                 }
+            }
+            __syncwarp();
+            if (b_active) {
+                mbar_wait(&p_bar[1], ph);
+                tc_fence_after();
+            }
+            if (elect_one()) {
                 if (b_active) {
-                    mbar_wait(&p_bar[1], ph);
-                    tc_fence_after();
-                    issue_pv(pb, vbase + st * Cfg::TILE, tO[1]);
+                    issue_pv(pb, vbase + st * TILE16, tO1);
                     umma_commit(&o_bar[1]);
                 }
                 umma_commit(&v_empty[st]);
                 if (more) {
                     if (b_active) {
-                        issue_qk(qb, kbase + nst * Cfg::TILE, tS[1]);
+                        issue_qk(qb, kbase + nst * TILE16, tS1);
                         umma_commit(&s_bar[1]);
                     }
                     umma_commit(&k_empty[nst]);
                 }
             }
+            __syncwarp();
         }
+    } else if (warp >= 10) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");  // idle warps of the control warpgroup
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ---------------------------------------------------------------- softmax warpgroups
         const int x = warp >> 2;  // 0 = tile A, 1 = tile B
         if (x == 0 || b_active) {
@@ -255,21 +271,40 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 const bool full = limit >= ATT_BN;
                 mbar_wait(&s_bar[x], ph);
                 tc_fence_after();
-                // pass 1: row max
+                // pass 1: row max. TMEM loads are double-buffered (the next chunk is in flight while this one is reduced)
+                // and four independent max chains keep the dependent-issue latency off the critical path.
                 float m_tile = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_s + c * 32, v);
+                {
+                    uint32_t va[32], vb[32];
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                    auto reduce = [&](const uint32_t (&v)[32], int c) {
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                                m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                                m2 = max3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                                m3 = max3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j < limit) m0 = fmaxf(m0, __uint_as_float(v[j]));
+                        }
+                    };
+                    tmem_ld_32x32(tmem_s, va);
                     tmem_ld_wait();
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) m_tile = max3(m_tile, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < limit) m_tile = fmaxf(m_tile, __uint_as_float(v[j]));
-                    }
+                    tmem_ld_32x32(tmem_s + 32, vb);
+                    reduce(va, 0);
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tmem_s + 64, va);
+                    reduce(vb, 1);
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tmem_s + 96, vb);
+                    reduce(va, 2);
+                    tmem_ld_wait();
+                    reduce(vb, 3);
+                    m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 }
                 const float m_new = fmaxf(m_run, m_tile);
                 const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
@@ -281,44 +316,57 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                     tc_fence_after();
                     o_update(alpha_prev);
                 }
-                // pass 2: p = 2^(s*scale*log2e - m*scale*log2e), bf16 into swizzled smem
-                float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_s + c * 32, v);
+                // pass 2: p = 2^(s*scale*log2e - m*scale*log2e), bf16 into swizzled smem (loads double-buffered again)
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                {
+                    uint32_t va[32], vb[32];
+                    auto emit = [&](const uint32_t (&v)[32], int c) {
+                        float p[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float t0, t1;
+                            fma2(t0, t1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), sl2, sl2, neg_ms, neg_ms);
+                            p[j] = ex2_approx(t0);
+                            p[j + 1] = ex2_approx(t1);
+                        }
+                        if (!full) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j >= limit) p[j] = 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            l0 += p[j];
+                            l1 += p[j + 1];
+                            l2 += p[j + 2];
+                            l3 += p[j + 3];
+                        }
+                        uint8_t* dst = p_row + (c >> 1) * 16384;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(p[i * 8 + 0], p[i * 8 + 1]);
+                            pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
+                            pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
+                            pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
+                            const int piece = (c & 1) * 4 + i;
+                            *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
+                        }
+                    };
+                    tmem_ld_32x32(tmem_s, va);
                     tmem_ld_wait();
-                    float p[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float t0, t1;
-                        fma2(t0, t1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), sl2, sl2, neg_ms, neg_ms);
-                        p[j] = ex2_approx(t0);
-                        p[j + 1] = ex2_approx(t1);
-                    }
-                    if (!full) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j >= limit) p[j] = 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        l0 += p[j];
-                        l1 += p[j + 1];
-                    }
-                    uint8_t* dst = p_row + (c >> 1) * 16384;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(p[i * 8 + 0], p[i * 8 + 1]);
-                        pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
-                        pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
-                        pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
-                        const int piece = (c & 1) * 4 + i;
-                        *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
-                    }
+                    tmem_ld_32x32(tmem_s + 32, vb);
+                    emit(va, 0);
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tmem_s + 64, va);
+                    emit(vb, 1);
+                    tmem_ld_wait();
+                    tmem_ld_32x32(tmem_s + 96, vb);
+                    emit(va, 2);
+                    tmem_ld_wait();
+                    emit(vb, 3);
                 }
-                l_run = l_run * alpha + (l0 + l1);
+                l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
                 m_run = m_new;
                 alpha_prev = alpha;
                 fence_proxy_async_smem();
