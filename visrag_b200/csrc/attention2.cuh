@@ -110,8 +110,10 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
     // Register rebalancing (per-SMSP register files: 12 warps x 168 regs at launch): the control warpgroup gives
     // registers away, the softmax warpgroups grow so that the O row (80 fp32) and two S chunks fit without spills.
     // Each setmaxnreg sits at the top of its own role branch (the allocator applies the limit to the code it dominates).
-    if (warp == 9) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (warp >= 8) {
+      // control warpgroup: ONE setmaxnreg executed by all four warps together (it is .sync.aligned per warpgroup)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+      if (warp == 9) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
             auto load_tile = [&](const CUtensorMap* m64, const CUtensorMap* m16, uint64_t* bar, uint8_t* dst, int col, int row) {
@@ -134,8 +136,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 load_tile(&maps.v64, &maps.v16, &v_full[st], smem + Cfg::OFF_V + st * Cfg::TILE, vcol, k_begin + j * ATT_BN);
             }
         }
-    } else if (warp == 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+      } else if (warp == 8) {
         // ------------------------------------------------------------ MMA issuer: the whole warp runs the (warp-uniform)
         // control flow, one elected lane issues each block of tcgen05.mma (keeps descriptors in uniform registers)
         constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 1, 0, 0);
@@ -221,8 +222,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             }
             __syncwarp();
         }
-    } else if (warp >= 10) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");  // idle warps of the control warpgroup
+      }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ---------------------------------------------------------------- softmax warpgroups

@@ -102,7 +102,10 @@ def gemm(
     e.rope_cols = rope_cols
     e.out = out.data_ptr()
     e.ldo = out.stride(0)
-    _launch("gemm", 2.0 * M * N * K, L.lib().vr_gemm_tuned, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.VR_BF16,
+    kind = "gemm" if _PROF is None else f"gemm:{M}x{N}x{K}:" + ("rope" if mode == L.VR_EPI_ROPE else "swiglu" if mode == L.VR_EPI_SWIGLU
+                                                               else ("gelu" if gelu else "") + ("+resid" if resid is not None else "") +
+                                                               ("f32" if out_dtype == torch.float32 else "bf16"))
+    _launch(kind, 2.0 * M * N * K, L.lib().vr_gemm_tuned, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.VR_BF16,
             M, N, K, C.byref(e), block_n, L.stream_ptr())
     return out
 
