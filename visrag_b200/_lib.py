@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvisrag_b200.so")
+LIB_PATH = os.environ.get("VR_LIB", os.path.join(_HERE, "libvisrag_b200.so"))  # VR_LIB: debug builds only
 
 VR_BF16, VR_F16, VR_F32 = 0, 1, 2
 VR_EPI_LINEAR, VR_EPI_ROPE, VR_EPI_SWIGLU = 0, 1, 2

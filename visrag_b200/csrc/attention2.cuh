@@ -18,6 +18,9 @@
 
 namespace vr {
 
+#ifndef VR_ATT2_SETMAXNREG
+#define VR_ATT2_SETMAXNREG 1
+#endif
 constexpr int ATT2_THREADS = 384;  // 2 softmax warpgroups + 1 control warpgroup (issuer, producer, 2 idle warps)
 
 template <int HS>
@@ -108,11 +111,13 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
     const uint32_t tmem_base = *tmem_slot;
 
     // Register rebalancing (per-SMSP register files: 12 warps x 168 regs at launch): the control warpgroup gives
-    // registers away, the softmax warpgroups grow so that the O row (80 fp32) and two S chunks fit without spills.
+    // registers away (168 -> 64), the softmax warpgroups grow (168 -> 208; 64*32 + 2*208*32 = 15360 <= 16384 per SMSP) so that the O row (80 fp32) and two S chunks fit without spills.
     // Each setmaxnreg sits at the top of its own role branch (the allocator applies the limit to the code it dominates).
     if (warp >= 8) {
       // control warpgroup: ONE setmaxnreg executed by all four warps together (it is .sync.aligned per warpgroup)
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+#if VR_ATT2_SETMAXNREG
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+#endif
       if (warp == 9) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
@@ -224,7 +229,9 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+#if VR_ATT2_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+#endif
         // ---------------------------------------------------------------- softmax warpgroups
         const int x = warp >> 2;  // 0 = tile A, 1 = tile B
         if (x == 0 || b_active) {

@@ -1,5 +1,6 @@
 #include "common.h"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 
 namespace vr {
 
@@ -21,6 +22,51 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int MODE, bool OUT_F32, bool GELU>
+static int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg;
+    CUtensorMap ta, tb;
+    if (int rc = make_tmap_2d(&ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, true)) return rc;
+    if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, true)) return rc;
+    auto kern = gemm2_tcgen05_kernel<MODE, OUT_F32, GELU>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ((g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((g.N + Cfg::BN - 1) / Cfg::BN);
+    const int pairs = num_sms() / 2;
+    const int clusters = tiles < pairs ? tiles : pairs;
+    kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
+    VR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// CTA-pair kernel (block_n == 2)
+static int dispatch_mode2(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s) {
+    const vr_gemm_epilogue& e = g.epi;
+    switch (e.mode) {
+        case VR_EPI_LINEAR:
+            if (e.out_dtype == VR_F32) {
+                VR_REQUIRE(!e.act_gelu, "vr_gemm: GELU epilogue writes bf16 only");
+                return launch_gemm2<VR_EPI_LINEAR, true, false>(A, lda, B, ldb, g, s);
+            }
+            VR_REQUIRE(e.out_dtype == VR_BF16, "vr_gemm: out_dtype must be VR_BF16 or VR_F32");
+            if (e.act_gelu) return launch_gemm2<VR_EPI_LINEAR, false, true>(A, lda, B, ldb, g, s);
+            return launch_gemm2<VR_EPI_LINEAR, false, false>(A, lda, B, ldb, g, s);
+        case VR_EPI_ROPE:
+            VR_REQUIRE(e.positions && e.rope_cos && e.rope_sin, "vr_gemm: ROPE epilogue needs positions/cos/sin");
+            VR_REQUIRE(g.N % 64 == 0 && e.rope_cols % 64 == 0, "vr_gemm: ROPE needs N and rope_cols multiples of 64");
+            return launch_gemm2<VR_EPI_ROPE, false, false>(A, lda, B, ldb, g, s);
+        case VR_EPI_SWIGLU:
+            VR_REQUIRE(g.N % 64 == 0, "vr_gemm: SWIGLU needs N multiple of 64");
+            return launch_gemm2<VR_EPI_SWIGLU, false, false>(A, lda, B, ldb, g, s);
+        default:
+            set_error("vr_gemm: unknown epilogue mode %d", e.mode);
+            return 2;
+    }
 }
 
 template <int BN>
@@ -66,9 +112,10 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int bn = block_n;
     if (bn == 0) bn = (N >= 256) ? 256 : 128;
+    if (bn == 2) return dispatch_mode2(A, lda, B, ldb, g, s);
     if (bn == 256) return dispatch_mode<256>(A, lda, B, ldb, g, s);
     if (bn == 128) return dispatch_mode<128>(A, lda, B, ldb, g, s);
-    set_error("vr_gemm: block_n must be 0, 128 or 256");
+    set_error("vr_gemm: block_n must be 0 (auto), 128, 256 or 2 (CTA-pair kernel)");
     return 2;
 }
 
