@@ -110,6 +110,62 @@ __global__ void norm_kernel(const float* __restrict__ x, long long ldx, const fl
     }
 }
 
+// Register-resident variant for dim == VPL * 128 (1152 -> VPL 9, 2304 -> VPL 18): the row is read from HBM exactly once.
+template <bool RMS, int VPL>
+__global__ void __launch_bounds__(256)
+norm_kernel_reg(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int rows, __nv_bfloat16* __restrict__ out, long long ldo, __nv_bfloat16* __restrict__ out2,
+                const float* __restrict__ add, int add_period) {
+    constexpr int DIM = VPL * 128;
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+        float4 v[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) v[i] = xr[lane + i * 32];
+        float mean = 0.f;
+        if (!RMS) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            mean = warp_sum(s) * (1.0f / DIM);
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.0f / DIM) + eps);
+        uint2* orow = reinterpret_cast<uint2*>(out + static_cast<long long>(row) * ldo);
+        uint2* orow2 = out2 ? reinterpret_cast<uint2*>(out2 + static_cast<long long>(row) * ldo) : nullptr;
+        const float4* arow = add ? reinterpret_cast<const float4*>(add + static_cast<long long>(row % add_period) * DIM) : nullptr;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + i * 32;
+            const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+            float y0 = (v[i].x - mean) * rstd * g.x, y1 = (v[i].y - mean) * rstd * g.y;
+            float y2 = (v[i].z - mean) * rstd * g.z, y3 = (v[i].w - mean) * rstd * g.w;
+            if (!RMS) {
+                const float4 bb = reinterpret_cast<const float4*>(beta)[c];
+                y0 += bb.x; y1 += bb.y; y2 += bb.z; y3 += bb.w;
+            }
+            uint2 pk;
+            pk.x = pack_bf16x2(y0, y1);
+            pk.y = pack_bf16x2(y2, y3);
+            orow[c] = pk;
+            if (orow2) {
+                const float4 aa = arow[c];
+                uint2 pk2;
+                pk2.x = pack_bf16x2(y0 + aa.x, y1 + aa.y);
+                pk2.y = pack_bf16x2(y2 + aa.z, y3 + aa.w);
+                orow2[c] = pk2;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LM input assembly: one warp per token row.
 // ---------------------------------------------------------------------------------------------
@@ -249,9 +305,15 @@ extern "C" int vr_layernorm(const float* x, int64_t ldx, const float* gamma, con
     VR_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "vr_layernorm: bad shape rows=%d dim=%d",
                rows, dim);
     VR_REQUIRE(!out2 || (add && add_period > 0), "vr_layernorm: out2 needs add/add_period");
-    norm_kernel<false><<<grid_for(rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, ldx, gamma, beta, eps, rows, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo,
-        reinterpret_cast<__nv_bfloat16*>(out2), add, add_period);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(out2);
+    if (dim == 1152)
+        norm_kernel_reg<false, 9><<<grid_for(rows, 8), 256, 0, s>>>(x, ldx, gamma, beta, eps, rows, o, ldo, o2, add, add_period);
+    else if (dim == 2304)
+        norm_kernel_reg<false, 18><<<grid_for(rows, 8), 256, 0, s>>>(x, ldx, gamma, beta, eps, rows, o, ldo, o2, add, add_period);
+    else
+        norm_kernel<false><<<grid_for(rows, 8), 256, 0, s>>>(x, ldx, gamma, beta, eps, rows, dim, o, ldo, o2, add, add_period);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -261,8 +323,12 @@ extern "C" int vr_rmsnorm(const float* x, int64_t ldx, const float* gamma, float
     VR_REQUIRE(x && gamma && out, "vr_rmsnorm: null pointer");
     VR_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "vr_rmsnorm: bad shape rows=%d dim=%d",
                rows, dim);
-    norm_kernel<true><<<grid_for(rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, ldx, gamma, nullptr, eps, rows, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo, nullptr, nullptr, 1);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (dim == 2304)
+        norm_kernel_reg<true, 18><<<grid_for(rows, 8), 256, 0, s>>>(x, ldx, gamma, nullptr, eps, rows, o, ldo, nullptr, nullptr, 1);
+    else
+        norm_kernel<true><<<grid_for(rows, 8), 256, 0, s>>>(x, ldx, gamma, nullptr, eps, rows, dim, o, ldo, nullptr, nullptr, 1);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -55,6 +55,37 @@ __device__ __forceinline__ float erf_as(float x) {
     return copysignf(fmaf(-p, e, 1.0f), x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+
+// two GELUs at once on the packed fp32x2 pipe (FFMA2): the fc1 epilogue is issue bound, this halves its FMA count
+__device__ __forceinline__ void pk_fma(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    unsigned long long A, B, Cc, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(Cc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(Cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    constexpr float R2 = 0.70710678118654752f;
+    const float a0 = fabsf(x0) * R2, a1 = fabsf(x1) * R2;  // |z|, z = x / sqrt(2)
+    float d0, d1, t0, t1, p0, p1, q0, q1, e0, e1, r0, r1;
+    pk_fma(d0, d1, a0, a1, 0.3275911f, 0.3275911f, 1.0f, 1.0f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+    pk_fma(p0, p1, t0, t1, 1.061405429f, 1.061405429f, -1.453152027f, -1.453152027f);
+    pk_fma(p0, p1, p0, p1, t0, t1, 1.421413741f, 1.421413741f);
+    pk_fma(p0, p1, p0, p1, t0, t1, -0.284496736f, -0.284496736f);
+    pk_fma(p0, p1, p0, p1, t0, t1, 0.254829592f, 0.254829592f);
+    pk_fma(p0, p1, p0, p1, t0, t1, 0.0f, 0.0f);
+    pk_fma(q0, q1, a0, a1, a0, a1, 0.0f, 0.0f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0 * -1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1 * -1.4426950408889634f));
+    pk_fma(r0, r1, p0, p1, -e0, -e1, 1.0f, 1.0f);  // erf(|z|)
+    r0 = copysignf(r0, x0);
+    r1 = copysignf(r1, x1);
+    const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+    pk_fma(x0, x1, h0, h1, r0, r1, h0, h1);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------
@@ -98,24 +129,24 @@ __device__ __forceinline__ void stage_store_wide(const uint8_t* st, int lane, T*
             *reinterpret_cast<uint4*>(gbase + static_cast<long long>(row0 + r) * ld + col0 + u * E) = q[i];
     }
 }
-// fp32 residual tile (32 rows x 32 columns of this warp): row-contiguous global loads into registers. Issued one chunk
-// AHEAD of its use (software prefetch), so the global latency overlaps the MMA wait / the previous chunk's processing.
-__device__ __forceinline__ void resid_prefetch(const GemmArgs& g, int lane, int row0, int col0, uint4 (&q)[8]) {
-    const vr_gemm_epilogue& e = g.epi;
+__device__ __forceinline__ void stage_load_wide_f32(uint8_t* st, int lane, const float* gbase, long long ld, int row0,
+                                                    int rows_valid, int col0, int cols_valid) {
     const int u = lane & 7;
-    const int rows_valid = g.M - row0, cols_valid = g.N - col0;
+    // all 8 global loads are issued before the first shared-memory store: the pointers may alias as far as the compiler
+    // knows, so interleaving load/store would serialise 8 full memory round trips per chunk
+    uint4 q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + (lane >> 3);
         q[i] = make_uint4(0, 0, 0, 0);
         if (r < rows_valid && u * 4 < cols_valid)
-            q[i] = *reinterpret_cast<const uint4*>(e.resid + static_cast<long long>(row0 + r) * e.ldo + col0 + u * 4);
+            q[i] = *reinterpret_cast<const uint4*>(gbase + static_cast<long long>(row0 + r) * ld + col0 + u * 4);
     }
-}
-__device__ __forceinline__ void stage_put_rows(uint8_t* st, int lane, const uint4 (&q)[8]) {
-    const int u = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(st + wide_off(i * 4 + (lane >> 3), u)) = q[i];
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        *reinterpret_cast<uint4*>(st + wide_off(r, u)) = q[i];
+    }
 }
 __device__ __forceinline__ void stage_put_half(uint8_t* st, int lane, const uint32_t (&w)[16]) {
 #pragma unroll
@@ -138,8 +169,7 @@ __device__ __forceinline__ void stage_store_half(const uint8_t* st, int lane, __
 
 // LINEAR: out = [resid +] scale * gelu?(acc + bias) [+ rowadd[row % period]]   (one 32-column chunk of one warp)
 template <bool OUT_F32, bool GELU>
-__device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&x)[32],
-                                           const uint4 (&rq)[8]) {
+__device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&x)[32]) {
     const vr_gemm_epilogue& e = g.epi;
     const int rows_valid = g.M - row0;          // may exceed 32
     const int cols_valid = g.N - col0;          // may exceed 32; N % 8 == 0
@@ -155,7 +185,7 @@ __device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int l
     }
     if (GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+        for (int j = 0; j < 32; j += 2) gelu_erf2(x[j], x[j + 1]);
     }
     if (e.scale != 1.0f) {
 #pragma unroll
@@ -172,7 +202,7 @@ __device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int l
         }
     }
     if (e.resid) {
-        stage_put_rows(st, lane, rq);  // prefetched by the caller
+        stage_load_wide_f32(st, lane, e.resid, e.ldo, row0, rows_valid, col0, cols_valid);
         __syncwarp();
         uint32_t w[32];
         stage_get_wide(st, lane, w);
@@ -366,12 +396,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
         const int half = ew >> 2;              // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;  // 128 or 64
-        const bool has_resid = MODE == VR_EPI_LINEAR && g.epi.resid != nullptr;
-        uint4 rq[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rq[i] = make_uint4(0, 0, 0, 0);
-        if (has_resid && static_cast<int>(blockIdx.x) < num_tiles)
-            resid_prefetch(g, lane, (blockIdx.x / tiles_n) * GEMM_BM + quarter * 32, (blockIdx.x % tiles_n) * BN + half * COLS_PER_WARP, rq);
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -384,33 +408,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
             if (MODE == VR_EPI_LINEAR) {
-                constexpr int NCHUNK = COLS_PER_WARP / 32;
 #pragma unroll 1
-                for (int c = 0; c < NCHUNK; ++c) {
+                for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + c * 32, r);
                     tmem_ld_wait();
-                    if (c == NCHUNK - 1) {
+                    if (c == COLS_PER_WARP / 32 - 1) {
                         // all of this warp's TMEM reads for the tile are done: hand the stage back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                     }
-                    uint4 cur[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cur[i] = rq[i];
-                    if (has_resid) {  // prefetch the residual of the NEXT chunk (or of the next tile's first chunk)
-                        if (c + 1 < NCHUNK) {
-                            resid_prefetch(g, lane, row0, n0 + half * COLS_PER_WARP + (c + 1) * 32, rq);
-                        } else if (t + static_cast<int>(gridDim.x) < num_tiles) {
-                            const int tn = t + gridDim.x;
-                            resid_prefetch(g, lane, (tn / tiles_n) * GEMM_BM + quarter * 32, (tn % tiles_n) * BN + half * COLS_PER_WARP, rq);
-                        }
-                    }
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v, cur);
+                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
                 }
             } else {
 #pragma unroll 1

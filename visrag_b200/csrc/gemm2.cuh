@@ -134,13 +134,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int half = ew >> 2;
         constexpr int COLS_PER_WARP = BN / 2;
         uint8_t* st = smem_stage + ew * Cfg::EPI_STAGE_BYTES;
-        const bool has_resid = MODE == VR_EPI_LINEAR && g.epi.resid != nullptr;
-        uint4 rq[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rq[i] = make_uint4(0, 0, 0, 0);
-        if (has_resid && cluster_id < num_tiles)
-            resid_prefetch(g, lane, (cluster_id / tiles_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32,
-                           (cluster_id % tiles_n) * BN + half * COLS_PER_WARP, rq);
         int it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
             const int acc = it & 1;
@@ -153,33 +146,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
             if (MODE == VR_EPI_LINEAR) {
-                constexpr int NCHUNK = COLS_PER_WARP / 32;
 #pragma unroll 1
-                for (int c = 0; c < NCHUNK; ++c) {
+                for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + c * 32, r);
                     tmem_ld_wait();
-                    if (c == NCHUNK - 1) {
+                    if (c == COLS_PER_WARP / 32 - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(ltempty);
                     }
-                    uint4 cur[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cur[i] = rq[i];
-                    if (has_resid) {
-                        if (c + 1 < NCHUNK) {
-                            resid_prefetch(g, lane, row0, n0 + half * COLS_PER_WARP + (c + 1) * 32, rq);
-                        } else if (t + num_clusters < num_tiles) {
-                            const int tn = t + num_clusters;
-                            resid_prefetch(g, lane, (tn / tiles_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32,
-                                           (tn % tiles_n) * BN + half * COLS_PER_WARP, rq);
-                        }
-                    }
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v, cur);
+                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
                 }
             } else {
 #pragma unroll 1

@@ -75,15 +75,21 @@ def plan_slices(width: int, height: int, cfg: VisRAGConfig) -> SlicePlan:
     return SlicePlan(_fit((width, height), S, P, False), (cols, rows), refine, (int(refine[0] / cols), int(refine[1] / rows)))
 
 
+def _rgb_array(image) -> np.ndarray:
+    return np.asarray(image, dtype=np.uint8)
+
+
 def render_slices(image, plan: SlicePlan) -> List[np.ndarray]:
     """Execute a plan with PIL bicubic resampling. Returns uint8 HWC arrays in LM order
     [thumbnail, row0col0, row0col1, ...] (`modeling_minicpmv.py:263-269`)."""
     from PIL import Image
 
     image = image.convert("RGB") if image.mode != "RGB" else image
-    out = [np.asarray(image.resize(plan.source_size, Image.Resampling.BICUBIC), dtype=np.uint8)]
+    # PIL's resize to the identical size is a plain copy: skip it (same pixels)
+    src = image if image.size == plan.source_size else image.resize(plan.source_size, Image.Resampling.BICUBIC)
+    out = [_rgb_array(src)]
     if plan.grid is not None:
-        refined = np.asarray(image.resize(plan.refine_size, Image.Resampling.BICUBIC), dtype=np.uint8)
+        refined = _rgb_array(image.resize(plan.refine_size, Image.Resampling.BICUBIC))
         cw, ch = plan.cell_size
         for i in range(plan.grid[1]):
             for j in range(plan.grid[0]):
@@ -103,8 +109,24 @@ def placeholder_text(plan: Optional[SlicePlan], tokenizer, query_num: int) -> st
     return text
 
 
+_TOK_CACHE: Dict[Tuple[int, str, Optional[int]], Tuple[np.ndarray, np.ndarray]] = {}
+
+
 def tokenize(content: str, tokenizer, max_inp_length: Optional[int]) -> Tuple[np.ndarray, np.ndarray]:
-    """ids (int32) truncated to max_inp_length and image_bound [n,2] = (index after <image>, index of </image>)."""
+    """ids (int32) truncated to max_inp_length and image_bound [n,2] = (index after <image>, index of </image>).
+    Pure function of (tokenizer, content, max length): results are memoised (every single-slice page shares one
+    placeholder string, so a corpus batch tokenises it once)."""
+    key = (id(tokenizer), content, max_inp_length)
+    hit = _TOK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    out = _tokenize(content, tokenizer, max_inp_length)
+    if len(_TOK_CACHE) < 4096:
+        _TOK_CACHE[key] = out
+    return out
+
+
+def _tokenize(content: str, tokenizer, max_inp_length: Optional[int]) -> Tuple[np.ndarray, np.ndarray]:
     ids = list(tokenizer.encode(content))
     if not tokenizer.add_bos_token:
         ids = [tokenizer.bos_id] + ids
@@ -144,15 +166,26 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
         raise ValueError("texts and images must have the same length")
     per_item_slices: List[List[np.ndarray]] = []
     ids_list, bound_list = [], []
-    for text, image in zip(texts, images):
+    for text in texts:
         if not isinstance(text, str):
             raise NotImplementedError(f"chatml format expected, expect outmost type to be str but got {type(text)}")
+
+    def one(item):
+        text, image = item
         if image:
             plan = plan_slices(image.size[0], image.size[1], cfg)
-            slices = render_slices(image, plan)
-            content = placeholder_text(plan, tokenizer, cfg.query_num) + "\n" + text
-        else:
-            slices, content = [], text
+            return render_slices(image, plan), placeholder_text(plan, tokenizer, cfg.query_num) + "\n" + text
+        return [], text
+
+    n_img = sum(1 for im in images if im)
+    if n_img >= 8:  # PIL resampling / packing release the GIL; the reference uses ThreadPoolExecutor(8) here too
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            prepared = list(ex.map(one, zip(texts, images)))
+    else:
+        prepared = [one(it) for it in zip(texts, images)]
+    for slices, content in prepared:
         ids, bound = tokenize(content, tokenizer, max_inp_length)
         if len(bound) > len(slices):
             raise ValueError("more <image> spans in the text than slices")
