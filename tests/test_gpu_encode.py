@@ -164,3 +164,38 @@ def test_config1_pipeline_encode_shards_retrieve_trec_metrics(tmp_path):
         qrels[f"q{qi}"] = {ranked[0][0]: 1}
     m = I.save_results(str(tmp_path), qrels, run2)
     assert m["recall_10"] == 1.0 and m["mrr_10"] == 1.0 and m["ndcg_cut_10"] == 1.0
+
+
+def test_mixed_resolution_corpus_recall_parity():
+    """BASELINE configs[4] in miniature: pages with sides in [336, 1344] (1..10 slices, many distinct grids), dynamic
+    grouping by geometry, Recall@1/5/10 of the engine's run vs the oracle's run on the same (query, corpus) set."""
+    from oracle import restated as O
+    from visrag_b200 import retriever as R
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.synth import synth_queries
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    cfg = VisRAGConfig.tiny()
+    sd = random_state_dict(cfg, 606)
+    tok = StubTokenizer(cfg.vocab)
+    rs = np.random.RandomState(44)
+    sizes = [(int(rs.randint(336, 1345)), int(rs.randint(336, 1345))) for _ in range(14)] + [(1344, 1344), (336, 336), (448, 1344)]
+    pages = synth_pages(sizes, 45)
+    queries = synth_queries(6, 46)
+    model = _engine_model(cfg, sd)
+    _, p = model.encode_passage(_items([""] * len(pages), pages, "d"), tokenizer=tok, max_inp_length=2048)
+    _, q = model.encode_query(_items(queries, [None] * len(queries), "q"), tokenizer=tok, max_inp_length=2048)
+    p_ref = O.encode(sd, cfg, tok, [""] * len(pages), pages)
+    q_ref = O.encode(sd, cfg, tok, queries, [None] * len(queries))
+    assert cosine_rows(p.cpu().numpy(), p_ref).min() >= COS_MIN and cosine_rows(q.cpu().numpy(), q_ref).min() >= COS_MIN
+    s_ref, i_ref = O.score_topk(q_ref, p_ref, 10)
+    _, i_run = R.score_topk(q, R.build_index(p), 10)
+    i_run = i_run.cpu().numpy()
+    relevant = [{int(i_ref[qi, 0])} for qi in range(len(queries))]          # planted relevance = the oracle's best page
+    for k in (1, 5, 10):
+        assert O.recall_at_k(i_run, relevant, k) == O.recall_at_k(i_ref, relevant, k) == 1.0
+    # identical top-10 up to bf16 near-ties (score gap below 2e-3)
+    full = q_ref @ p_ref.T
+    for qi in range(len(queries)):
+        assert (full[qi, i_run[qi]] >= s_ref[qi, -1] - 2e-3).all()

@@ -121,6 +121,22 @@ def _stage_attention_body(torch, ops):
         x = qkv.view(S, N, 3, nh, hs)[..., :hd].permute(2, 0, 3, 1, 4)  # [3,S,nh,N,hd]
         want = _attn_ref(x[0], x[1], x[2], hd ** -0.5, False).permute(0, 2, 1, 3).reshape(S * N, nh * hd)
         ok &= report(f"attn vit S={S} N={N} heads={nh}", out, want, 2e-2)
+    # --- growing row maxima: later key tiles carry much larger scores, which forces the lazy O rescale in TMEM
+    for (S, N, nh) in [(2, 512, 2), (1, 1024, 3)]:
+        hd, hs = 72, 80
+        qkv = torch.zeros(S * N, 3, nh, hs, device=dev)
+        qkv[..., :hd] = torch.randn(S * N, 3, nh, hd, device=dev)
+        ramp = torch.linspace(0.2, 6.0, N, device=dev).repeat(S)[:, None, None]   # key scale grows with position
+        qkv[:, 1, :, :hd] *= ramp
+        qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
+        cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=dev)
+        out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device=dev)
+        ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
+                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out)
+        torch.cuda.synchronize()
+        x = qkv.view(S, N, 3, nh, hs)[..., :hd].permute(2, 0, 3, 1, 4)
+        want = _attn_ref(x[0], x[1], x[2], hd ** -0.5, False).permute(0, 2, 1, 3).reshape(S * N, nh * hd)
+        ok &= report(f"attn vit growing-max S={S} N={N} heads={nh}", out, want, 2e-2)
     # --- LM style: causal var-len, hd 64
     for lens in ([68], [1, 5, 68, 127, 128, 129, 300], [670, 33]):
         nh, hd = 4, 64

@@ -8,8 +8,9 @@
 //                S_A(j+1) is issued as soon as tile A's softmax(j) has consumed S_A(j), i.e. while tile B is still in
 //                its softmax: tensor core and SFU work overlap inside one CTA.
 //   warp  9    : TMA producer (one lane): Q_A, Q_B once; K_j / V_j through two-stage full/empty mbarrier rings.
-// The O accumulator lives in registers (O = O*alpha + PV, PV read back from TMEM); that update for iteration j is
-// deferred to iteration j+1 (after the row-max pass) so the P.V MMA latency is hidden behind SFU/ALU work.
+// The O accumulator stays in TMEM for the whole key loop (P.V MMAs accumulate into it); the softmax keeps a lazy
+// reference maximum and rescales O in place (tcgen05.ld/st) only when a row maximum grows by more than 2^8, so the
+// whole S row fits in registers and is read from TMEM exactly once per key block.
 // Per-element ALU cost is cut with the sm_100 packed/3-input forms: FMNMX3 (max), FFMA2 (scale), FADD2 (sum), ex2.approx.
 //
 // TMEM (512 columns): S_A [0,128)  S_B [128,256)  PV_A [256,256+HS)  PV_B [384,384+HS).
@@ -165,15 +166,17 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 }
             if (C1::HAS16) umma_f16_ss(d_tmem, hi32 | (q16 + C1::NCH * 1024), hi32 | (k16 + C1::NCH * 1024), idesc_qk, acc);
         };
-        auto issue_pv = [&](uint32_t p16, uint32_t v16, uint32_t d_tmem) {
+        // O (+)= P V : O lives in TMEM for the whole key loop; the first key block overwrites, later ones accumulate
+        auto issue_pv = [&](uint32_t p16, uint32_t v16, uint32_t d_tmem, uint32_t first_block) {
 #pragma unroll
             for (int kk = 0; kk < ATT_BN / 16; ++kk) {
                 const uint64_t pd = hi128 | (p16 + (kk >> 2) * 1024 + (kk & 3) * 2);
+                const uint32_t accum = (kk != 0 || !first_block) ? 1u : 0u;
 #pragma unroll
                 for (int c = 0; c < C1::NCH; ++c)
-                    umma_f16_ss(d_tmem + c * 64, pd, hi128 | (v16 + c * 1024 + kk * 128), idesc_pv64, kk != 0);
+                    umma_f16_ss(d_tmem + c * 64, pd, hi128 | (v16 + c * 1024 + kk * 128), idesc_pv64, accum);
                 if (C1::HAS16)
-                    umma_f16_ss(d_tmem + C1::NCH * 64, pd, hi32 | (v16 + C1::NCH * 1024 + kk * 32), idesc_pv16, kk != 0);
+                    umma_f16_ss(d_tmem + C1::NCH * 64, pd, hi32 | (v16 + C1::NCH * 1024 + kk * 32), idesc_pv16, accum);
             }
         };
         const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 384;
@@ -199,7 +202,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             if (more) mbar_wait(&k_full[nst], nuse_parity);
             tc_fence_after();
             if (elect_one()) {
-                issue_pv(pa, vbase + st * TILE16, tO0);
+                issue_pv(pa, vbase + st * TILE16, tO0, j == 0);
                 umma_commit(&o_bar[0]);
                 if (more) {
                     issue_qk(qa, kbase + nst * TILE16, tS0);
@@ -213,7 +216,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             }
             if (elect_one()) {
                 if (b_active) {
-                    issue_pv(pb, vbase + st * TILE16, tO1);
+                    issue_pv(pb, vbase + st * TILE16, tO1, j == 0);
                     umma_commit(&o_bar[1]);
                 }
                 umma_commit(&v_empty[st]);
@@ -242,33 +245,12 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             const uint32_t tmem_o = tmem_base + 256 + x * 128 + lane_off;
             const int causal_shift = len_k - len_q;
             const float sl2 = a.scale_log2;
-            float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-            float o[HS];
-#pragma unroll
-            for (int j = 0; j < HS; ++j) o[j] = 0.f;
+            // Online softmax with a LAZY reference maximum (the FlashAttention-4 trick): O accumulates in TMEM and is only
+            // rescaled when the row maximum grows by more than 2^RESCALE_LOG2 relative to the reference; otherwise the
+            // stale reference is kept (p <= 2^8 stays harmless in bf16/fp32, and O/l is invariant to the reference).
+            constexpr float RESCALE_LOG2 = 8.0f;
+            float m_ref = -INFINITY, l_run = 0.f;
             uint8_t* p_row = smem + (x ? Cfg::OFF_PB : Cfg::OFF_PA) + (r >> 3) * 1024 + (r & 7) * 128;
-
-            auto o_update = [&](float alpha) {
-#pragma unroll
-                for (int c = 0; c < HS / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_o + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2)
-                        fma2(o[c * 32 + j], o[c * 32 + j + 1], o[c * 32 + j], o[c * 32 + j + 1], alpha, alpha,
-                             __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                }
-                if (HS % 32 == 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x16(tmem_o + (HS / 32) * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2)
-                        fma2(o[(HS / 32) * 32 + j], o[(HS / 32) * 32 + j + 1], o[(HS / 32) * 32 + j], o[(HS / 32) * 32 + j + 1],
-                             alpha, alpha, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                }
-            };
 
             for (int kt = 0; kt < nkt; ++kt) {
                 const uint32_t ph = kt & 1;
@@ -278,125 +260,150 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 const bool full = limit >= ATT_BN;
                 mbar_wait(&s_bar[x], ph);
                 tc_fence_after();
-                // pass 1: row max. TMEM loads are double-buffered (the next chunk is in flight while this one is reduced)
-                // and four independent max chains keep the dependent-issue latency off the critical path.
-                float m_tile = -INFINITY;
+                // the whole S row (128 fp32) comes to registers in one go: O is in TMEM, so there is room
+                uint32_t sv[4][32];
+                tmem_ld_32x32(tmem_s, sv[0]);
+                tmem_ld_32x32(tmem_s + 32, sv[1]);
+                tmem_ld_32x32(tmem_s + 64, sv[2]);
+                tmem_ld_32x32(tmem_s + 96, sv[3]);
+                tmem_ld_wait();
+                float m_tile;
                 {
-                    uint32_t va[32], vb[32];
                     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-                    auto reduce = [&](const uint32_t (&v)[32], int c) {
-                        if (full) {
+                    if (full) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
-                                m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                                m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                                m2 = max3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                                m3 = max3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                                m0 = max3(m0, __uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]));
+                                m1 = max3(m1, __uint_as_float(sv[c][j + 2]), __uint_as_float(sv[c][j + 3]));
+                                m2 = max3(m2, __uint_as_float(sv[c][j + 4]), __uint_as_float(sv[c][j + 5]));
+                                m3 = max3(m3, __uint_as_float(sv[c][j + 6]), __uint_as_float(sv[c][j + 7]));
                             }
-                        } else {
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (c * 32 + j < limit) m0 = fmaxf(m0, __uint_as_float(v[j]));
-                        }
-                    };
-                    tmem_ld_32x32(tmem_s, va);
-                    tmem_ld_wait();
-                    tmem_ld_32x32(tmem_s + 32, vb);
-                    reduce(va, 0);
-                    tmem_ld_wait();
-                    tmem_ld_32x32(tmem_s + 64, va);
-                    reduce(vb, 1);
-                    tmem_ld_wait();
-                    tmem_ld_32x32(tmem_s + 96, vb);
-                    reduce(va, 2);
-                    tmem_ld_wait();
-                    reduce(vb, 3);
+                                if (c * 32 + j < limit) m0 = fmaxf(m0, __uint_as_float(sv[c][j]));
+                    }
                     m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 }
-                const float m_new = fmaxf(m_run, m_tile);
-                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-                const float alpha = ex2_approx((m_run - m_use) * sl2);
-                const float neg_ms = -m_use * sl2;
-                // deferred O update of the previous key block (its P.V MMA ran behind pass 1); also frees P smem
+                // previous P.V must have retired before P smem is overwritten (and before O is rescaled)
                 if (kt > 0) {
                     mbar_wait(&o_bar[x], ph ^ 1);
                     tc_fence_after();
-                    o_update(alpha_prev);
                 }
-                // pass 2: p = 2^(s*scale*log2e - m*scale*log2e), bf16 into swizzled smem (loads double-buffered again)
+                // lazy rescale: only when some row of this warp outgrew its reference by more than 2^8
+                const bool grow = (m_tile - m_ref) * sl2 > RESCALE_LOG2;  // false for m_tile = -inf; true for m_ref = -inf
+                if (kt == 0) {
+                    m_ref = (m_tile == -INFINITY) ? 0.f : m_tile;
+                } else if (__any_sync(0xffffffffu, grow)) {
+                    const float alpha = grow ? ex2_approx((m_ref - m_tile) * sl2) : 1.0f;
+                    if (grow) {
+                        m_ref = m_tile;
+                        l_run *= alpha;
+                    }
+#pragma unroll
+                    for (int c = 0; c < HS / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_o + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                        tmem_st_32x32(tmem_o + c * 32, v);
+                    }
+                    if (HS % 32 == 16) {
+                        uint32_t v[16];
+                        tmem_ld_32x16(tmem_o + (HS / 32) * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                        tmem_st_32x16(tmem_o + (HS / 32) * 32, v);
+                    }
+                    tmem_st_wait();
+                }
+                const float neg_ms = -m_ref * sl2;
+                // p = 2^(s*scale*log2e - m_ref*scale*log2e), bf16 into the 128B-swizzled P tile
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                {
-                    uint32_t va[32], vb[32];
-                    auto emit = [&](const uint32_t (&v)[32], int c) {
-                        float p[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float t0, t1;
-                            fma2(t0, t1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), sl2, sl2, neg_ms, neg_ms);
-                            p[j] = ex2_approx(t0);
-                            p[j + 1] = ex2_approx(t1);
-                        }
-                        if (!full) {
+                for (int c = 0; c < 4; ++c) {
+                    float p[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (c * 32 + j >= limit) p[j] = 0.f;
-                        }
+                    for (int j = 0; j < 32; j += 2) {
+                        float t0, t1;
+                        fma2(t0, t1, __uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]), sl2, sl2, neg_ms, neg_ms);
+                        p[j] = ex2_approx(t0);
+                        p[j + 1] = ex2_approx(t1);
+                    }
+                    if (!full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            l0 += p[j];
-                            l1 += p[j + 1];
-                            l2 += p[j + 2];
-                            l3 += p[j + 3];
-                        }
-                        uint8_t* dst = p_row + (c >> 1) * 16384;
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j >= limit) p[j] = 0.f;
+                    }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 pk;
-                            pk.x = pack_bf16x2(p[i * 8 + 0], p[i * 8 + 1]);
-                            pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
-                            pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
-                            pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
-                            const int piece = (c & 1) * 4 + i;
-                            *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
-                        }
-                    };
-                    tmem_ld_32x32(tmem_s, va);
-                    tmem_ld_wait();
-                    tmem_ld_32x32(tmem_s + 32, vb);
-                    emit(va, 0);
-                    tmem_ld_wait();
-                    tmem_ld_32x32(tmem_s + 64, va);
-                    emit(vb, 1);
-                    tmem_ld_wait();
-                    tmem_ld_32x32(tmem_s + 96, vb);
-                    emit(va, 2);
-                    tmem_ld_wait();
-                    emit(vb, 3);
+                    for (int j = 0; j < 32; j += 4) {
+                        l0 += p[j];
+                        l1 += p[j + 1];
+                        l2 += p[j + 2];
+                        l3 += p[j + 3];
+                    }
+                    uint8_t* dst = p_row + (c >> 1) * 16384;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(p[i * 8 + 0], p[i * 8 + 1]);
+                        pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
+                        pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
+                        pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
+                        const int piece = (c & 1) * 4 + i;
+                        *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
+                    }
                 }
-                l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
-                m_run = m_new;
-                alpha_prev = alpha;
+                l_run += (l0 + l1) + (l2 + l3);
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&p_bar[x]);
             }
+            // ---- O / l : read the accumulator once, after the last P.V
             mbar_wait(&o_bar[x], (nkt - 1) & 1);
             tc_fence_after();
-            // the last block's alpha was already folded into l_run; O still needs it
-            o_update(alpha_prev);
-            if (q_idx < len_q) {
+            {  // TMEM loads are warp collective: every lane reads, only valid rows store
                 const float inv = 1.0f / l_run;
                 const long long row = a.cu_q ? (long long)(q_begin + q_idx) : (long long)b * a.max_q + q_idx;
                 __nv_bfloat16* dst = a.out + row * a.ldo + head * a.head_dim;
+                const bool valid = q_idx < len_q;
 #pragma unroll
-                for (int j8 = 0; j8 < HS / 8; ++j8) {
-                    if (j8 * 8 < a.head_dim) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(o[j8 * 8 + 0] * inv, o[j8 * 8 + 1] * inv);
-                        pk.y = pack_bf16x2(o[j8 * 8 + 2] * inv, o[j8 * 8 + 3] * inv);
-                        pk.z = pack_bf16x2(o[j8 * 8 + 4] * inv, o[j8 * 8 + 5] * inv);
-                        pk.w = pack_bf16x2(o[j8 * 8 + 6] * inv, o[j8 * 8 + 7] * inv);
-                        *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
+                for (int c = 0; c < HS / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_o + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (valid && c * 32 + j8 * 8 < a.head_dim) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
+                            pk.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
+                            pk.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
+                            pk.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
+                            *reinterpret_cast<uint4*>(dst + c * 32 + j8 * 8) = pk;
+                        }
+                    }
+                }
+                if (HS % 32 == 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(tmem_o + (HS / 32) * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j8 = 0; j8 < 2; ++j8) {
+                        if (valid && (HS / 32) * 32 + j8 * 8 < a.head_dim) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
+                            pk.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
+                            pk.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
+                            pk.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
+                            *reinterpret_cast<uint4*>(dst + (HS / 32) * 32 + j8 * 8) = pk;
+                        }
                     }
                 }
             }
