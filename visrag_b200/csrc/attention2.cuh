@@ -113,12 +113,13 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
     const uint32_t tmem_base = *tmem_slot;
 
     // Register rebalancing (per-SMSP register files: 12 warps x 168 regs at launch): the control warpgroup gives
-    // registers away (168 -> 64), the softmax warpgroups grow (168 -> 208; 64*32 + 2*208*32 = 15360 <= 16384 per SMSP) so that the O row (80 fp32) and two S chunks fit without spills.
+    // registers away (96 -> 48), the softmax warpgroups grow (96 -> 104); per scheduler 48*32 + 4*104*32 = 14848 of 16384: the
+    // increase only succeeds with some slack left (an exactly-full register file deadlocked on hardware), so that the O row (80 fp32) and two S chunks fit without spills.
     // Each setmaxnreg sits at the top of its own role branch (the allocator applies the limit to the code it dominates).
     if (warp >= 16) {
       // control warpgroup: ONE setmaxnreg executed by all four warps together (it is .sync.aligned per warpgroup)
 #if VR_ATT2_SETMAXNREG
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
 #endif
       if (warp == 17) {
         if (lane == 0) {
@@ -234,7 +235,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
       }
     } else {
 #if VR_ATT2_SETMAXNREG
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
 #endif
         // ---------------------------------------------------------------- softmax warpgroups
         // Query tile x (0 = A, 1 = B) is served by TWO warpgroups: thread (x, h, r) owns the key columns [64h, 64h+64) of
