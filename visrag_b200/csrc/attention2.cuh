@@ -2,12 +2,12 @@
 //
 // The softmax of a 128x128 score tile needs 16384 exp2 on the SFU (MUFU: 16/clk/SM => 1024 cycles), more than the two
 // MMAs of the tile (640 cycles at head stride 80), so the design goal is to keep the SFUs busy all the time:
-//   warps 0-7  : softmax of query tile A: two warpgroups, thread (h, r) = key columns [64h, 64h+64) of query row r
-//   warps 8-15 : softmax of query tile B
-//   warp  16   : MMA issuer (one lane): S_x = Q_x K_j^T into TMEM, PV_x = P_x V_j into TMEM, x in {A, B}.
+//   warps 0-3  : softmax of query tile A (thread = one query row, S read from TMEM with tcgen05.ld)
+//   warps 4-7  : softmax of query tile B
+//   warp  8    : MMA issuer (one lane): S_x = Q_x K_j^T into TMEM, PV_x = P_x V_j into TMEM, x in {A, B}.
 //                S_A(j+1) is issued as soon as tile A's softmax(j) has consumed S_A(j), i.e. while tile B is still in
 //                its softmax: tensor core and SFU work overlap inside one CTA.
-//   warp  17   : TMA producer (one lane): Q_A, Q_B once; K_j / V_j through two-stage full/empty mbarrier rings.
+//   warp  9    : TMA producer (one lane): Q_A, Q_B once; K_j / V_j through two-stage full/empty mbarrier rings.
 // The O accumulator stays in TMEM for the whole key loop (P.V MMAs accumulate into it); the softmax keeps a lazy
 // reference maximum and rescales O in place (tcgen05.ld/st) only when a row maximum grows by more than 2^8, so the
 // whole S row fits in registers and is read from TMEM exactly once per key block.
@@ -22,7 +22,7 @@ namespace vr {
 #ifndef VR_ATT2_SETMAXNREG
 #define VR_ATT2_SETMAXNREG 1
 #endif
-constexpr int ATT2_THREADS = 640;  // 4 softmax warpgroups (2 per query tile: each row is shared by 2 threads) + 1 control warpgroup
+constexpr int ATT2_THREADS = 384;  // 2 softmax warpgroups + 1 control warpgroup (issuer, producer, 2 idle warps)
 
 template <int HS>
 struct Att2Cfg {
@@ -36,8 +36,7 @@ struct Att2Cfg {
     static constexpr int OFF_PA = 6 * TILE;
     static constexpr int OFF_PB = 6 * TILE + 32768;
     static constexpr int OFF_BAR = 6 * TILE + 65536;
-    static constexpr int OFF_XCH = OFF_BAR + 256;            // row max / row sum exchange between the two threads of a row
-    static constexpr int SMEM_BYTES = OFF_XCH + 2 * 2 * 2 * 128 * 4 + 1024;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -101,27 +100,26 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_bar[i], 1);
-            mbar_init(&p_bar[i], 256);
+            mbar_init(&p_bar[i], 128);
             mbar_init(&o_bar[i], 1);
         }
         fence_mbar_init();
     }
-    if (warp == 16) tmem_alloc<512>(tmem_slot);
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     // Register rebalancing (per-SMSP register files: 12 warps x 168 regs at launch): the control warpgroup gives
-    // registers away (96 -> 48), the softmax warpgroups grow (96 -> 104); per scheduler 48*32 + 4*104*32 = 14848 of 16384: the
-    // increase only succeeds with some slack left (an exactly-full register file deadlocked on hardware), so that the O row (80 fp32) and two S chunks fit without spills.
+    // registers away (168 -> 64), the softmax warpgroups grow (168 -> 208; 64*32 + 2*208*32 = 15360 <= 16384 per SMSP) so that the O row (80 fp32) and two S chunks fit without spills.
     // Each setmaxnreg sits at the top of its own role branch (the allocator applies the limit to the code it dominates).
-    if (warp >= 16) {
+    if (warp >= 8) {
       // control warpgroup: ONE setmaxnreg executed by all four warps together (it is .sync.aligned per warpgroup)
 #if VR_ATT2_SETMAXNREG
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
 #endif
-      if (warp == 17) {
+      if (warp == 9) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
             auto load_tile = [&](const CUtensorMap* m64, const CUtensorMap* m16, uint64_t* bar, uint8_t* dst, int col, int row) {
@@ -144,7 +142,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 load_tile(&maps.v64, &maps.v16, &v_full[st], smem + Cfg::OFF_V + st * Cfg::TILE, vcol, k_begin + j * ATT_BN);
             }
         }
-      } else if (warp == 16) {
+      } else if (warp == 8) {
         // ------------------------------------------------------------ MMA issuer: the whole warp runs the (warp-uniform)
         // control flow, one elected lane issues each block of tcgen05.mma (keeps descriptors in uniform registers)
         constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 1, 0, 0);
@@ -235,20 +233,15 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
       }
     } else {
 #if VR_ATT2_SETMAXNREG
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
 #endif
         // ---------------------------------------------------------------- softmax warpgroups
-        // Query tile x (0 = A, 1 = B) is served by TWO warpgroups: thread (x, h, r) owns the key columns [64h, 64h+64) of
-        // row r. Twice as many warps per scheduler hide the TMEM / SFU / dependent-issue latencies that dominated the
-        // one-thread-per-row version; the two threads of a row exchange their partial row maximum through shared memory
-        // (one 256-thread named barrier per key block) and only combine their partial row sums at the very end.
-        const int x = warp >> 3;
-        const int h = (warp >> 2) & 1;
+        const int x = warp >> 2;  // 0 = tile A, 1 = tile B
         if (x == 0 || b_active) {
-            const int r = (warp & 3) * 32 + lane;
+            const int r = threadIdx.x & 127;
             const int q_idx = q0 + x * ATT_BM + r;
             const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-            const uint32_t tmem_s = tmem_base + x * 128 + h * 64 + lane_off;
+            const uint32_t tmem_s = tmem_base + x * 128 + lane_off;
             const uint32_t tmem_o = tmem_base + 256 + x * 128 + lane_off;
             const int causal_shift = len_k - len_q;
             const float sl2 = a.scale_log2;
@@ -257,28 +250,29 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             // stale reference is kept (p <= 2^8 stays harmless in bf16/fp32, and O/l is invariant to the reference).
             constexpr float RESCALE_LOG2 = 8.0f;
             float m_ref = -INFINITY, l_run = 0.f;
-            uint8_t* p_row = smem + (x ? Cfg::OFF_PB : Cfg::OFF_PA) + h * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-            float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_XCH);  // [2 buffers][2 tiles][2 halves][128]
-            const int bar_id = 1 + x;
+            uint8_t* p_row = smem + (x ? Cfg::OFF_PB : Cfg::OFF_PA) + (r >> 3) * 1024 + (r & 7) * 128;
 
             for (int kt = 0; kt < nkt; ++kt) {
                 const uint32_t ph = kt & 1;
-                const int key0 = kt * ATT_BN + h * 64;
-                int limit = len_k - key0;                     // this thread's columns [0, limit) of its 64 exist
+                const int key0 = kt * ATT_BN;
+                int limit = len_k - key0;
                 if (CAUSAL) limit = min(limit, q_idx + causal_shift - key0 + 1);
-                const bool full = limit >= 64;
+                const bool full = limit >= ATT_BN;
                 mbar_wait(&s_bar[x], ph);
                 tc_fence_after();
-                uint32_t sv[2][32];
+                // the whole S row (128 fp32) comes to registers in one go: O is in TMEM, so there is room
+                uint32_t sv[4][32];
                 tmem_ld_32x32(tmem_s, sv[0]);
                 tmem_ld_32x32(tmem_s + 32, sv[1]);
+                tmem_ld_32x32(tmem_s + 64, sv[2]);
+                tmem_ld_32x32(tmem_s + 96, sv[3]);
                 tmem_ld_wait();
-                float m_part;
+                float m_tile;
                 {
                     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
                     if (full) {
 #pragma unroll
-                        for (int c = 0; c < 2; ++c)
+                        for (int c = 0; c < 4; ++c)
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
                                 m0 = max3(m0, __uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]));
@@ -288,25 +282,20 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                             }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 2; ++c)
+                        for (int c = 0; c < 4; ++c)
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (c * 32 + j < limit) m0 = fmaxf(m0, __uint_as_float(sv[c][j]));
                     }
-                    m_part = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 }
-                // row maximum of the whole 128-key block = max over the two halves
-                float* xb = xch + ((kt & 1) * 2 + x) * 256;
-                xb[h * 128 + r] = m_part;
-                asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-                const float m_tile = fmaxf(m_part, xb[(h ^ 1) * 128 + r]);
                 // previous P.V must have retired before P smem is overwritten (and before O is rescaled)
                 if (kt > 0) {
                     mbar_wait(&o_bar[x], ph ^ 1);
                     tc_fence_after();
                 }
-                // lazy rescale: both threads of a row take the same decision; each rescales its share of the O columns
-                const bool grow = (m_tile - m_ref) * sl2 > RESCALE_LOG2;
+                // lazy rescale: only when some row of this warp outgrew its reference by more than 2^8
+                const bool grow = (m_tile - m_ref) * sl2 > RESCALE_LOG2;  // false for m_tile = -inf; true for m_ref = -inf
                 if (kt == 0) {
                     m_ref = (m_tile == -INFINITY) ? 0.f : m_tile;
                 } else if (__any_sync(0xffffffffu, grow)) {
@@ -315,29 +304,30 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                         m_ref = m_tile;
                         l_run *= alpha;
                     }
-                    {   // columns [32h, 32h+32)
+#pragma unroll
+                    for (int c = 0; c < HS / 32; ++c) {
                         uint32_t v[32];
-                        tmem_ld_32x32(tmem_o + h * 32, v);
+                        tmem_ld_32x32(tmem_o + c * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                        tmem_st_32x32(tmem_o + h * 32, v);
+                        tmem_st_32x32(tmem_o + c * 32, v);
                     }
-                    if (HS == 80 && h == 0) {   // the 16-wide tail chunk
+                    if (HS % 32 == 16) {
                         uint32_t v[16];
-                        tmem_ld_32x16(tmem_o + 64, v);
+                        tmem_ld_32x16(tmem_o + (HS / 32) * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                        tmem_st_32x16(tmem_o + 64, v);
+                        tmem_st_32x16(tmem_o + (HS / 32) * 32, v);
                     }
                     tmem_st_wait();
                 }
                 const float neg_ms = -m_ref * sl2;
-                // p = 2^(s*scale*log2e - m_ref*scale*log2e), bf16 into this thread's 64-key half of the swizzled P tile
+                // p = 2^(s*scale*log2e - m_ref*scale*log2e), bf16 into the 128B-swizzled P tile
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     float p[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
@@ -358,6 +348,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                         l2 += p[j + 2];
                         l3 += p[j + 3];
                     }
+                    uint8_t* dst = p_row + (c >> 1) * 16384;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         uint4 pk;
@@ -365,8 +356,8 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                         pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
                         pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
                         pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
-                        const int piece = c * 4 + i;
-                        *reinterpret_cast<uint4*>(p_row + ((piece ^ (r & 7)) << 4)) = pk;
+                        const int piece = (c & 1) * 4 + i;
+                        *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
                     }
                 }
                 l_run += (l0 + l1) + (l2 + l3);
@@ -374,13 +365,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 tc_fence_before();
                 mbar_arrive(&p_bar[x]);
             }
-            // ---- row sum = sum of the two halves; then O / l, each thread storing its share of the head's columns
-            {
-                float* xb = xch + ((nkt & 1) * 2 + x) * 256;
-                xb[h * 128 + r] = l_run;
-                asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-                l_run += xb[(h ^ 1) * 128 + r];
-            }
+            // ---- O / l : read the accumulator once, after the last P.V
             mbar_wait(&o_bar[x], (nkt - 1) & 1);
             tc_fence_after();
             {  // TMEM loads are warp collective: every lane reads, only valid rows store
@@ -388,35 +373,36 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 const long long row = a.cu_q ? (long long)(q_begin + q_idx) : (long long)b * a.max_q + q_idx;
                 __nv_bfloat16* dst = a.out + row * a.ldo + head * a.head_dim;
                 const bool valid = q_idx < len_q;
-                {
+#pragma unroll
+                for (int c = 0; c < HS / 32; ++c) {
                     uint32_t v[32];
-                    tmem_ld_32x32(tmem_o + h * 32, v);
+                    tmem_ld_32x32(tmem_o + c * 32, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
-                        if (valid && h * 32 + j8 * 8 < a.head_dim) {
+                        if (valid && c * 32 + j8 * 8 < a.head_dim) {
                             uint4 pk;
                             pk.x = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
                             pk.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
                             pk.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
                             pk.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
-                            *reinterpret_cast<uint4*>(dst + h * 32 + j8 * 8) = pk;
+                            *reinterpret_cast<uint4*>(dst + c * 32 + j8 * 8) = pk;
                         }
                     }
                 }
-                if (HS == 80 && h == 0) {
+                if (HS % 32 == 16) {
                     uint32_t v[16];
-                    tmem_ld_32x16(tmem_o + 64, v);
+                    tmem_ld_32x16(tmem_o + (HS / 32) * 32, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j8 = 0; j8 < 2; ++j8) {
-                        if (valid && 64 + j8 * 8 < a.head_dim) {
+                        if (valid && (HS / 32) * 32 + j8 * 8 < a.head_dim) {
                             uint4 pk;
                             pk.x = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
                             pk.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
                             pk.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
                             pk.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
-                            *reinterpret_cast<uint4*>(dst + 64 + j8 * 8) = pk;
+                            *reinterpret_cast<uint4*>(dst + (HS / 32) * 32 + j8 * 8) = pk;
                         }
                     }
                 }
@@ -426,7 +412,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
