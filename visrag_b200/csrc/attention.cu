@@ -2,6 +2,7 @@
 #include "common.h"
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 
 namespace vr {
 
@@ -28,16 +29,26 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
     a.ldo = p.ldo;
     if constexpr (V2) {
-        // two 128-query tiles per CTA in ping-pong (sequences longer than one tile: the ViT)
-        using Cfg2 = Att2Cfg<HS>;
-        auto kern = attention2_tcgen05_kernel<HS, CAUSAL>;
+        // sequences longer than one query tile: two 128-query tiles per CTA, 64-key blocks, double-buffered S / P
+        using Cfg3 = Att3Cfg<HS>;
+        AttMaps3 m3;
+        memset(&m3, 0, sizeof(m3));
+        m3.q64 = maps.q64;
+        m3.q16 = maps.q16;
+        if (int rc = make_tmap_2d(&m3.k64, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 64, 128, true)) return rc;
+        if (int rc = make_tmap_2d(&m3.v64, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 64, 128, true)) return rc;
+        if (Cfg::HAS16) {
+            if (int rc = make_tmap_2d(&m3.k16, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 16, 32, true)) return rc;
+            if (int rc = make_tmap_2d(&m3.v16, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 16, 32, true)) return rc;
+        }
+        auto kern = attention3_tcgen05_kernel<HS, CAUSAL>;
         static bool attr_set = false;
         if (!attr_set) {
-            VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+            VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
             attr_set = true;
         }
         dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
-        kern<<<grid, ATT2_THREADS, Cfg2::SMEM_BYTES, stream>>>(maps, a);
+        kern<<<grid, ATT3_THREADS, Cfg3::SMEM_BYTES, stream>>>(m3, a);
     } else {
         auto kern = attention_tcgen05_kernel<HS, CAUSAL>;
         static bool attr_set = false;

@@ -19,6 +19,9 @@
 
 namespace vr {
 
+#ifndef VR_ATT_ABL
+#define VR_ATT_ABL 0  // timing ablations (debug builds only): 1 no exp2, 2 no P stores, 3 no TMEM S loads, 4 no row max
+#endif
 #ifndef VR_ATT2_SETMAXNREG
 #define VR_ATT2_SETMAXNREG 1
 #endif
@@ -262,11 +265,18 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 tc_fence_after();
                 // the whole S row (128 fp32) comes to registers in one go: O is in TMEM, so there is room
                 uint32_t sv[4][32];
+#if VR_ATT_ABL == 3
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sv[c][j] = __float_as_uint(0.01f * (c * 32 + j + kt));
+#else
                 tmem_ld_32x32(tmem_s, sv[0]);
                 tmem_ld_32x32(tmem_s + 32, sv[1]);
                 tmem_ld_32x32(tmem_s + 64, sv[2]);
                 tmem_ld_32x32(tmem_s + 96, sv[3]);
                 tmem_ld_wait();
+#endif
                 float m_tile;
                 {
                     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -333,8 +343,13 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                     for (int j = 0; j < 32; j += 2) {
                         float t0, t1;
                         fma2(t0, t1, __uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]), sl2, sl2, neg_ms, neg_ms);
+#if VR_ATT_ABL == 1
+                        p[j] = t0 * 0.001f;
+                        p[j + 1] = t1 * 0.001f;
+#else
                         p[j] = ex2_approx(t0);
                         p[j + 1] = ex2_approx(t1);
+#endif
                     }
                     if (!full) {
 #pragma unroll
@@ -357,6 +372,9 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                         pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
                         pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
                         const int piece = (c & 1) * 4 + i;
+#if VR_ATT_ABL == 2
+                        if (pk.x == 0x12345678u)
+#endif
                         *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
                     }
                 }
