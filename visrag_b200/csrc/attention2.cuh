@@ -36,9 +36,7 @@ struct Att2Cfg {
     static constexpr int OFF_QB = TILE;
     static constexpr int OFF_K = 2 * TILE;   // 2 stages
     static constexpr int OFF_V = 4 * TILE;   // 2 stages
-    static constexpr int OFF_PA = 6 * TILE;
-    static constexpr int OFF_PB = 6 * TILE + 32768;
-    static constexpr int OFF_BAR = 6 * TILE + 65536;
+    static constexpr int OFF_BAR = 6 * TILE;
     static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
@@ -155,7 +153,6 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
         const uint64_t hi32 = make_smem_desc(0, 16, 256, kLayoutSW32);
         const uint32_t qa = smem_u32(smem + Cfg::OFF_QA) >> 4, qb = smem_u32(smem + Cfg::OFF_QB) >> 4;
         const uint32_t kbase = smem_u32(smem + Cfg::OFF_K) >> 4, vbase = smem_u32(smem + Cfg::OFF_V) >> 4;
-        const uint32_t pa = smem_u32(smem + Cfg::OFF_PA) >> 4, pb = smem_u32(smem + Cfg::OFF_PB) >> 4;
         constexpr uint32_t TILE16 = Cfg::TILE >> 4;
         // all addresses below are in 16-byte units (the descriptor's address field)
         auto issue_qk = [&](uint32_t q16, uint32_t k16, uint32_t d_tmem) {
@@ -169,17 +166,21 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 }
             if (C1::HAS16) umma_f16_ss(d_tmem, hi32 | (q16 + C1::NCH * 1024), hi32 | (k16 + C1::NCH * 1024), idesc_qk, acc);
         };
-        // O (+)= P V : O lives in TMEM for the whole key loop; the first key block overwrites, later ones accumulate
-        auto issue_pv = [&](uint32_t p16, uint32_t v16, uint32_t d_tmem, uint32_t first_block) {
+        // O (+)= P V : O lives in TMEM for the whole key loop; the first key block overwrites, later ones accumulate.
+        // P is the A operand and is read from TENSOR MEMORY (it was written there by the softmax warps, packed bf16x2,
+        // over the first 64 columns of the tile's own S region): an A operand in shared memory costs 128 rows x 32 B per
+        // MMA regardless of N (~128 cycles), which made the 16 small-N P.V MMAs of a key block 4x more expensive than
+        // their math (measured: every smem-A variant of this kernel sat at ~1.27 ms per ViT layer).
+        auto issue_pv = [&](uint32_t p_tmem, uint32_t v16, uint32_t d_tmem, uint32_t first_block) {
 #pragma unroll
             for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-                const uint64_t pd = hi128 | (p16 + (kk >> 2) * 1024 + (kk & 3) * 2);
+                const uint32_t pa_t = p_tmem + kk * 8;  // 16 keys = 8 packed 32-bit columns per k-step
                 const uint32_t accum = (kk != 0 || !first_block) ? 1u : 0u;
 #pragma unroll
                 for (int c = 0; c < C1::NCH; ++c)
-                    umma_f16_ss(d_tmem + c * 64, pd, hi128 | (v16 + c * 1024 + kk * 128), idesc_pv64, accum);
+                    umma_f16_ts(d_tmem + c * 64, pa_t, hi128 | (v16 + c * 1024 + kk * 128), idesc_pv64, accum);
                 if (C1::HAS16)
-                    umma_f16_ss(d_tmem + C1::NCH * 64, pd, hi32 | (v16 + C1::NCH * 1024 + kk * 32), idesc_pv16, accum);
+                    umma_f16_ts(d_tmem + C1::NCH * 64, pa_t, hi32 | (v16 + C1::NCH * 1024 + kk * 32), idesc_pv16, accum);
             }
         };
         const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 384;
@@ -205,7 +206,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             if (more) mbar_wait(&k_full[nst], nuse_parity);
             tc_fence_after();
             if (elect_one()) {
-                issue_pv(pa, vbase + st * TILE16, tO0, j == 0);
+                issue_pv(tS0, vbase + st * TILE16, tO0, j == 0);
                 umma_commit(&o_bar[0]);
                 if (more) {
                     issue_qk(qa, kbase + nst * TILE16, tS0);
@@ -219,7 +220,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             }
             if (elect_one()) {
                 if (b_active) {
-                    issue_pv(pb, vbase + st * TILE16, tO1, j == 0);
+                    issue_pv(tS1, vbase + st * TILE16, tO1, j == 0);
                     umma_commit(&o_bar[1]);
                 }
                 umma_commit(&v_empty[st]);
@@ -253,7 +254,6 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             // stale reference is kept (p <= 2^8 stays harmless in bf16/fp32, and O/l is invariant to the reference).
             constexpr float RESCALE_LOG2 = 8.0f;
             float m_ref = -INFINITY, l_run = 0.f;
-            uint8_t* p_row = smem + (x ? Cfg::OFF_PB : Cfg::OFF_PA) + (r >> 3) * 1024 + (r & 7) * 128;
 
             for (int kt = 0; kt < nkt; ++kt) {
                 const uint32_t ph = kt & 1;
@@ -363,23 +363,15 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                         l2 += p[j + 2];
                         l3 += p[j + 3];
                     }
-                    uint8_t* dst = p_row + (c >> 1) * 16384;
+                    // packed bf16x2 -> TMEM columns [16c, 16c+16) of this tile's S region (the row's S values are already
+                    // in registers, and the tensor core only overwrites S again after P.V has consumed P)
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(p[i * 8 + 0], p[i * 8 + 1]);
-                        pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
-                        pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
-                        pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
-                        const int piece = (c & 1) * 4 + i;
-#if VR_ATT_ABL == 2
-                        if (pk.x == 0x12345678u)
-#endif
-                        *reinterpret_cast<uint4*>(dst + ((piece ^ (r & 7)) << 4)) = pk;
-                    }
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
+                    tmem_st_32x16(tmem_s + c * 16, pk);
                 }
                 l_run += (l0 + l1) + (l2 + l3);
-                fence_proxy_async_smem();
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_bar[x]);
             }
