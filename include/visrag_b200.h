@@ -96,8 +96,8 @@ typedef struct {
 } vr_attn_params;
 
 int vr_attention(const vr_attn_params* p, void* stream);
-/* test hook: 1 = always use the one-tile-per-CTA kernel (the two-tile ping-pong kernel is the default for max_q > 128) */
-void vr_attention_force_v1(int32_t on);
+/* test hook: 0 = default, 1 = always use the one-tile-per-CTA kernel, 3 = experimental 64-key-block kernel */
+void vr_attention_force_v1(int32_t variant);
 
 
 /* ------------------------------------------------------------------------------------

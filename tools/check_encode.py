@@ -185,7 +185,7 @@ def stage_attention_perf():
     qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
     cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device="cuda")
     out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device="cuda")
-    for force in (0, 1):
+    for force in (0, 3, 1):
         L.lib().vr_attention_force_v1(force)
 
         def run():
@@ -201,7 +201,7 @@ def stage_attention_perf():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"attention {'v1' if force else 'v2'}: {ms:.3f} ms  {4.0 * N * N * nh * hd * S / ms / 1e9:.1f} TFLOP/s (useful)", flush=True)
+        print(f"attention variant {force}: {ms:.3f} ms  {4.0 * N * N * nh * hd * S / ms / 1e9:.1f} TFLOP/s (useful)", flush=True)
     L.lib().vr_attention_force_v1(0)
     return True
 

@@ -6,6 +6,8 @@
 
 namespace vr {
 
+static int g_variant = 0;  // see vr_attention_force_v1()
+
 template <int HS, bool CAUSAL, bool V2>
 static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     using Cfg = AttCfg<HS>;
@@ -29,26 +31,39 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
     a.ldo = p.ldo;
     if constexpr (V2) {
-        // sequences longer than one query tile: two 128-query tiles per CTA, 64-key blocks, double-buffered S / P
-        using Cfg3 = Att3Cfg<HS>;
-        AttMaps3 m3;
-        memset(&m3, 0, sizeof(m3));
-        m3.q64 = maps.q64;
-        m3.q16 = maps.q16;
-        if (int rc = make_tmap_2d(&m3.k64, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 64, 128, true)) return rc;
-        if (int rc = make_tmap_2d(&m3.v64, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 64, 128, true)) return rc;
-        if (Cfg::HAS16) {
-            if (int rc = make_tmap_2d(&m3.k16, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 16, 32, true)) return rc;
-            if (int rc = make_tmap_2d(&m3.v16, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 16, 32, true)) return rc;
+        if (g_variant == 3) {
+            // experimental: 64-key blocks, double-buffered S / P in shared memory (attention3.cuh)
+            using Cfg3 = Att3Cfg<HS>;
+            AttMaps3 m3;
+            memset(&m3, 0, sizeof(m3));
+            m3.q64 = maps.q64;
+            m3.q16 = maps.q16;
+            if (int rc = make_tmap_2d(&m3.k64, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 64, 128, true)) return rc;
+            if (int rc = make_tmap_2d(&m3.v64, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 64, 128, true)) return rc;
+            if (Cfg::HAS16) {
+                if (int rc = make_tmap_2d(&m3.k16, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 16, 32, true)) return rc;
+                if (int rc = make_tmap_2d(&m3.v16, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 16, 32, true)) return rc;
+            }
+            auto kern = attention3_tcgen05_kernel<HS, CAUSAL>;
+            static bool attr_set3 = false;
+            if (!attr_set3) {
+                VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
+                attr_set3 = true;
+            }
+            dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
+            kern<<<grid, ATT3_THREADS, Cfg3::SMEM_BYTES, stream>>>(m3, a);
+        } else {
+            // sequences longer than one query tile: two 128-query tiles per CTA in ping-pong, P and O in tensor memory
+            using Cfg2 = Att2Cfg<HS>;
+            auto kern = attention2_tcgen05_kernel<HS, CAUSAL>;
+            static bool attr_set = false;
+            if (!attr_set) {
+                VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+                attr_set = true;
+            }
+            dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
+            kern<<<grid, ATT2_THREADS, Cfg2::SMEM_BYTES, stream>>>(maps, a);
         }
-        auto kern = attention3_tcgen05_kernel<HS, CAUSAL>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
-            attr_set = true;
-        }
-        dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
-        kern<<<grid, ATT3_THREADS, Cfg3::SMEM_BYTES, stream>>>(m3, a);
     } else {
         auto kern = attention_tcgen05_kernel<HS, CAUSAL>;
         static bool attr_set = false;
@@ -63,12 +78,10 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     return 0;
 }
 
-static bool g_force_v1 = false;
-
 }  // namespace vr
 
-// test hook: force the single-tile kernel for every shape (lets the tests cover both kernels on the same inputs)
-extern "C" void vr_attention_force_v1(int32_t on) { vr::g_force_v1 = on != 0; }
+// test hook: 0 = default kernels, 1 = force the single-tile kernel for every shape, 3 = experimental attention3 kernel
+extern "C" void vr_attention_force_v1(int32_t variant) { vr::g_variant = variant; }
 
 extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
     using namespace vr;
@@ -80,7 +93,7 @@ extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
     VR_REQUIRE(p->ldo % 8 == 0, "vr_attention: ldo must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const bool c = p->causal != 0;
-    const bool v2 = p->max_q > ATT_BM && !g_force_v1;  // more than one query tile per sequence
+    const bool v2 = p->max_q > ATT_BM && g_variant != 1;  // more than one query tile per sequence
     switch (p->head_stride) {
         case 64:
             if (v2) return c ? launch_attention<64, true, true>(*p, s) : launch_attention<64, false, true>(*p, s);
