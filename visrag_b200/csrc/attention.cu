@@ -30,14 +30,14 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.scale_log2 = p.scale * 1.4426950408889634f;
     a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
     a.ldo = p.ldo;
+    a.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
+    a.ldq = p.ldq;
     if constexpr (V2) {
         if (g_variant == 3) {
             // experimental: 64-key blocks, double-buffered S / P in shared memory (attention3.cuh)
             using Cfg3 = Att3Cfg<HS>;
             AttMaps3 m3;
             memset(&m3, 0, sizeof(m3));
-            m3.q64 = maps.q64;
-            m3.q16 = maps.q16;
             if (int rc = make_tmap_2d(&m3.k64, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 64, 128, true)) return rc;
             if (int rc = make_tmap_2d(&m3.v64, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 64, 128, true)) return rc;
             if (Cfg::HAS16) {

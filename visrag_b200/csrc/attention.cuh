@@ -52,6 +52,8 @@ struct AttArgs {
     float scale_log2;  // scale * log2(e)
     __nv_bfloat16* out;
     long long ldo;
+    const __nv_bfloat16* q;  // query matrix base (kernels that stage Q themselves instead of through TMA)
+    long long ldq;
 };
 
 struct AttMaps {

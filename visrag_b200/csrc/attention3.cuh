@@ -8,14 +8,19 @@
 // budget: Q.K(j+1) runs while softmax(j) is still working, P.V(j) runs behind softmax(j+1), and the softmax warps
 // never wait for the tensor core in steady state.
 //
+// Both MMA A operands live in TENSOR MEMORY: an A operand in shared memory costs 128 rows x 32 B of smem reads per MMA
+// whatever N is (~128 cycles), which dominated the small-N MMAs of attention; from TMEM the cost follows N.
+//   * Q_x (128 x HS bf16 = HS/2 packed columns) is written once by the softmax warps (global -> registers -> tcgen05.st);
+//   * P_x(j) overwrites the first 32 columns of its own S buffer (the S row is already in registers by then).
+//
 //   warps 0-3 / 4-7 : softmax of query tile A / B (thread = one query row; S row of 64 fp32 read once from TMEM;
 //                     lazy-maximum online softmax; O accumulates in TMEM and is rescaled in place only when a row
 //                     maximum grows by more than 2^8)
 //   warp 8          : MMA issuer (warp-uniform control flow, one elected lane issues)
-//   warp 9          : TMA producer: Q_A, Q_B once; K_j / V_j (64 keys) through 4-stage full/empty mbarrier rings
+//   warp 9          : TMA producer: K_j / V_j (64 keys) through 4-stage full/empty mbarrier rings
 //
-// TMEM: S_x[b] at columns (2x+b)*64 (256 columns), O_A at 256, O_B at 384.
-// smem: Q_A Q_B | K ring x4 | V ring x4 | P_A[2] P_B[2] (128 x 64 bf16, 128B-swizzled) | barriers.
+// TMEM (496 of 512 columns): S_x[b] at (2x+b)*64 | O_A 256 | O_B 336 | Q_A 416 | Q_B 456.
+// smem: K ring x4 | V ring x4 | barriers.
 #pragma once
 #include "attention2.cuh"
 
@@ -29,20 +34,17 @@ template <int HS>
 struct Att3Cfg {
     using C1 = AttCfg<HS>;
     static_assert(HS == 64 || HS == 80, "built for head stride 64 / 80");
-    static constexpr int QTILE = C1::TILE_BYTES;                                   // 128 rows
     static constexpr int KTILE = C1::NCH * 8192 + (C1::HAS16 ? 2048 : 0);          // 64 rows
-    static constexpr int OFF_QA = 0;
-    static constexpr int OFF_QB = QTILE;
-    static constexpr int OFF_K = 2 * QTILE;
+    static constexpr int OFF_K = 0;
     static constexpr int OFF_V = OFF_K + ATT3_STAGES * KTILE;
-    static constexpr int OFF_P = OFF_V + ATT3_STAGES * KTILE;                      // P[x][b] : 16 KB each
-    static constexpr int OFF_BAR = OFF_P + 4 * 16384;
+    static constexpr int OFF_BAR = OFF_V + ATT3_STAGES * KTILE;
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-    static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && KTILE % 1024 == 0, "swizzle alignment");
+    static constexpr int TM_O = 256, TM_Q = 256 + 2 * HS;                          // TMEM columns
+    static_assert(TM_Q + HS <= 512, "TMEM budget");
+    static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && KTILE % 1024 == 0, "swizzle alignment");
 };
 
 struct AttMaps3 {
-    CUtensorMap q64, q16;      // 128-row boxes
     CUtensorMap k64, k16;      // 64-row boxes
     CUtensorMap v64, v16;      // 64-row boxes
 };
@@ -55,15 +57,15 @@ attention3_tcgen05_kernel(const __grid_constant__ AttMaps3 maps, const AttArgs a
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-    uint64_t* q_bar = bars + 0;
-    uint64_t* k_full = bars + 1;                    // [4]
-    uint64_t* k_empty = bars + 5;                   // [4]
-    uint64_t* v_full = bars + 9;                    // [4]
-    uint64_t* v_empty = bars + 13;                  // [4]
-    uint64_t* s_full = bars + 17;                   // [x][b]  S_x[b] holds Q_x K_j^T
-    uint64_t* p_full = bars + 21;                   // [x][b]  P_x[b] written (128 arrivals); implies S_x[b] was consumed
-    uint64_t* pv_done = bars + 25;                  // [x][b]  P.V that read P_x[b] retired (P buffer free, O up to date)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+    uint64_t* q_ready = bars + 0;                   // [x]     Q_x written to TMEM (128 arrivals)
+    uint64_t* k_full = bars + 2;                    // [4]
+    uint64_t* k_empty = bars + 6;                   // [4]
+    uint64_t* v_full = bars + 10;                   // [4]
+    uint64_t* v_empty = bars + 14;                  // [4]
+    uint64_t* s_full = bars + 18;                   // [x][b]  S_x[b] holds Q_x K_j^T
+    uint64_t* p_full = bars + 22;                   // [x][b]  P_x(j) written over S_x[b] (128 arrivals)
+    uint64_t* pv_done = bars + 26;                  // [x][b]  P.V that read P_x[b] retired (O up to date, S_x[b] reusable)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qp = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -81,7 +83,8 @@ attention3_tcgen05_kernel(const __grid_constant__ AttMaps3 maps, const AttArgs a
     }
 
     if (threadIdx.x == 0) {
-        mbar_init(q_bar, 1);
+        mbar_init(&q_ready[0], 128);
+        mbar_init(&q_ready[1], 128);
         for (int i = 0; i < ATT3_STAGES; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], 1);
@@ -110,10 +113,7 @@ attention3_tcgen05_kernel(const __grid_constant__ AttMaps3 maps, const AttArgs a
                 for (int c = 0; c < C1::NCH; ++c) tma_load_2d(m64, bar, dst + c * chunk_bytes, col + c * 64, row);
                 if (C1::HAS16) tma_load_2d(m16, bar, dst + C1::NCH * chunk_bytes, col + C1::NCH * 64, row);
             };
-            const int qcol = a.q_col0 + head * HS, kcol = a.k_col0 + head * HS, vcol = a.v_col0 + head * HS;
-            mbar_expect_tx(q_bar, Cfg::QTILE * (b_active ? 2 : 1));
-            load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QA, 16384, qcol, q_begin + q0);
-            if (b_active) load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QB, 16384, qcol, q_begin + q0 + ATT_BM);
+            const int kcol = a.k_col0 + head * HS, vcol = a.v_col0 + head * HS;
             for (int j = 0; j < nkt; ++j) {
                 const int st = j % ATT3_STAGES;
                 const uint32_t use_parity = (j / ATT3_STAGES) & 1;
@@ -132,42 +132,39 @@ attention3_tcgen05_kernel(const __grid_constant__ AttMaps3 maps, const AttArgs a
         constexpr uint32_t idesc_pv16 = make_idesc_f16(128, 16, 1, 0, 1);
         const uint64_t hi128 = make_smem_desc(0, 16, 1024, kLayoutSW128);
         const uint64_t hi32 = make_smem_desc(0, 16, 256, kLayoutSW32);
-        const uint32_t q16[2] = {smem_u32(smem + Cfg::OFF_QA) >> 4, smem_u32(smem + Cfg::OFF_QB) >> 4};
         const uint32_t kbase = smem_u32(smem + Cfg::OFF_K) >> 4, vbase = smem_u32(smem + Cfg::OFF_V) >> 4;
-        const uint32_t pbase = smem_u32(smem + Cfg::OFF_P) >> 4;
         constexpr uint32_t KT16 = Cfg::KTILE >> 4;
-        // S_x[buf] = Q_x K_j^T   (Q chunks are 128 rows x 64 dims = 16 KB apart, K chunks 64 rows x 64 dims = 8 KB apart)
+        // S_x[buf] = Q_x K_j^T : A = Q_x from TMEM (8 packed columns per 16-element k-step), B = K chunk (64 keys, K-major)
         auto issue_qk = [&](int x, int j) {
-            const uint32_t qa = q16[x], ka = kbase + (j % ATT3_STAGES) * KT16;
+            const uint32_t qt = tmem_base + Cfg::TM_Q + x * (HS / 2), ka = kbase + (j % ATT3_STAGES) * KT16;
             const uint32_t d_tmem = tmem_base + (2 * x + (j & 1)) * 64;
             uint32_t acc = 0;
 #pragma unroll
             for (int c = 0; c < C1::NCH; ++c)
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    umma_f16_ss(d_tmem, hi128 | (qa + c * 1024 + kk * 2), hi128 | (ka + c * 512 + kk * 2), idesc_qk, acc);
+                    umma_f16_ts(d_tmem, qt + (c * 4 + kk) * 8, hi128 | (ka + c * 512 + kk * 2), idesc_qk, acc);
                     acc = 1;
                 }
-            if (C1::HAS16) umma_f16_ss(d_tmem, hi32 | (qa + C1::NCH * 1024), hi32 | (ka + C1::NCH * 512), idesc_qk, acc);
+            if (C1::HAS16) umma_f16_ts(d_tmem, qt + C1::NCH * 32, hi32 | (ka + C1::NCH * 512), idesc_qk, acc);
             umma_commit(&s_full[2 * x + (j & 1)]);
         };
-        // O_x (+)= P_x[buf] V_j   (V chunk: 64 keys x 64 dims, 128 B per key row, MN-major; 16 keys = 2048 B per k-step)
+        // O_x (+)= P_x(j) V_j : A = P from TMEM (first 32 columns of S_x[j&1]); V chunk: 64 keys x 64 dims, MN-major
         auto issue_pv = [&](int x, int j) {
-            const uint32_t pa = pbase + (2 * x + (j & 1)) * 1024, va = vbase + (j % ATT3_STAGES) * KT16;
-            const uint32_t d_tmem = tmem_base + 256 + x * 128;
+            const uint32_t pt = tmem_base + (2 * x + (j & 1)) * 64, va = vbase + (j % ATT3_STAGES) * KT16;
+            const uint32_t d_tmem = tmem_base + Cfg::TM_O + x * HS;
 #pragma unroll
             for (int kk = 0; kk < ATT3_BN / 16; ++kk) {
-                const uint64_t pd = hi128 | (pa + kk * 2);
                 const uint32_t accum = (kk != 0 || j != 0) ? 1u : 0u;
 #pragma unroll
                 for (int c = 0; c < C1::NCH; ++c)
-                    umma_f16_ss(d_tmem + c * 64, pd, hi128 | (va + c * 512 + kk * 128), idesc_pv64, accum);
-                if (C1::HAS16) umma_f16_ss(d_tmem + C1::NCH * 64, pd, hi32 | (va + C1::NCH * 512 + kk * 32), idesc_pv16, accum);
+                    umma_f16_ts(d_tmem + c * 64, pt + kk * 8, hi128 | (va + c * 512 + kk * 128), idesc_pv64, accum);
+                if (C1::HAS16) umma_f16_ts(d_tmem + C1::NCH * 64, pt + kk * 8, hi32 | (va + C1::NCH * 512 + kk * 32), idesc_pv16, accum);
             }
             umma_commit(&pv_done[2 * x + (j & 1)]);
         };
         const int ntile = b_active ? 2 : 1;
-        mbar_wait(q_bar, 0);
+        for (int x = 0; x < ntile; ++x) mbar_wait(&q_ready[x], 0);
         // prologue: S(0) and S(1) of both tiles
         for (int j = 0; j < 2 && j < nkt; ++j) {
             mbar_wait(&k_full[j % ATT3_STAGES], 0);
@@ -205,12 +202,35 @@ attention3_tcgen05_kernel(const __grid_constant__ AttMaps3 maps, const AttArgs a
             const int r = threadIdx.x & 127;
             const int q_idx = q0 + x * ATT_BM + r;
             const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-            const uint32_t tmem_o = tmem_base + 256 + x * 128 + lane_off;
+            const uint32_t tmem_o = tmem_base + Cfg::TM_O + x * HS + lane_off;
             const int causal_shift = len_k - len_q;
             const float sl2 = a.scale_log2;
             constexpr float RESCALE_LOG2 = 8.0f;
             float m_ref = -INFINITY, l_run = 0.f;
-            uint8_t* p_row0 = smem + Cfg::OFF_P + (2 * x) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+            {   // this row of Q: global -> registers -> TMEM (packed bf16x2, HS/2 columns); rows past the sequence are zero
+                const uint32_t tmem_q = tmem_base + Cfg::TM_Q + x * (HS / 2) + lane_off;
+                const uint4* src = reinterpret_cast<const uint4*>(a.q + static_cast<long long>(q_begin + q_idx) * a.ldq + a.q_col0 + head * HS);
+                const bool valid = q_idx < len_q;
+                uint32_t w[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t = valid ? src[i] : make_uint4(0, 0, 0, 0);
+                    w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+                }
+                tmem_st_32x32(tmem_q, w);
+                if (HS == 80) {
+                    uint32_t w2[8];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint4 t = valid ? src[8 + i] : make_uint4(0, 0, 0, 0);
+                        w2[4 * i] = t.x; w2[4 * i + 1] = t.y; w2[4 * i + 2] = t.z; w2[4 * i + 3] = t.w;
+                    }
+                    tmem_st_32x8(tmem_q + 32, w2);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&q_ready[x]);
+            }
 
             for (int kt = 0; kt < nkt; ++kt) {
                 const int buf = kt & 1;
@@ -279,14 +299,12 @@ attention3_tcgen05_kernel(const __grid_constant__ AttMaps3 maps, const AttArgs a
                     }
                     tmem_st_wait();
                 }
-                // the P buffer is free once the P.V of two blocks ago has retired
-                if (kt >= 2) {
-                    mbar_wait(&pv_done[2 * x + buf], buf_parity ^ 1);
-                    tc_fence_after();
-                }
+                // P overwrites the first 32 columns of this S buffer: the tensor core last touched it with Q.K(kt) itself.
+                // (The P.V of two blocks ago on this buffer has necessarily retired - Q.K(kt) was issued behind it - but its
+                // mbarrier phase is still consumed here so that every phase of pv_done is observed in order.)
+                if (kt >= 2) mbar_wait(&pv_done[2 * x + buf], buf_parity ^ 1);
                 const float neg_ms = -m_ref * sl2;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                uint8_t* p_row = p_row0 + buf * 16384;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     float p[32];
@@ -309,19 +327,13 @@ attention3_tcgen05_kernel(const __grid_constant__ AttMaps3 maps, const AttArgs a
                         l2 += p[j + 2];
                         l3 += p[j + 3];
                     }
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(p[i * 8 + 0], p[i * 8 + 1]);
-                        pk.y = pack_bf16x2(p[i * 8 + 2], p[i * 8 + 3]);
-                        pk.z = pack_bf16x2(p[i * 8 + 4], p[i * 8 + 5]);
-                        pk.w = pack_bf16x2(p[i * 8 + 6], p[i * 8 + 7]);
-                        const int piece = c * 4 + i;
-                        *reinterpret_cast<uint4*>(p_row + ((piece ^ (r & 7)) << 4)) = pk;
-                    }
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
+                    tmem_st_32x16(tmem_s + c * 16, pk);
                 }
                 l_run += (l0 + l1) + (l2 + l3);
-                fence_proxy_async_smem();
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_full[2 * x + buf]);
             }
