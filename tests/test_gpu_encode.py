@@ -114,6 +114,31 @@ def test_batch_composition_does_not_change_results():
     assert eng.encode([], [], tok).shape == (0, cfg.hidden)
 
 
+def test_encode_stream_equals_blocking_calls():
+    """The pipelined loop (prep of batch i+1 on a worker thread, async D2H) returns exactly what one blocking
+    model(passage=...) call per batch returns, in order, including a ragged last batch and an empty dataset."""
+    from visrag_b200 import inference as I
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    cfg = VisRAGConfig.tiny()
+    model = _engine_model(cfg, random_state_dict(cfg, 3))
+    tok = StubTokenizer(cfg.vocab)
+    pages = synth_pages([(448, 448), (300, 500), (700, 900), (224, 224), (448, 448), (640, 320), (500, 500)], 21)
+    data = [{"id": f"p{i}", "text": "", "image": im} for i, im in enumerate(pages)]
+    kw = {"tokenizer": tok, "max_inp_length": 2048}
+    got_ids, got = [], []
+    for ids, arr in I.encode_stream(I._batches(data, 3), model, kw):
+        got_ids += ids
+        got.append(arr)
+    assert got_ids == [d["id"] for d in data] and [len(g) for g in got] == [3, 3, 1]
+    for b, batch in enumerate(I._batches(data, 3)):
+        want = model(passage=batch, **kw).p_reps.cpu().numpy()
+        assert np.array_equal(got[b], want)
+    assert list(I.encode_stream([], model, kw)) == []
+
+
 def test_config1_pipeline_encode_shards_retrieve_trec_metrics(tmp_path):
     """BASELINE configs[0]: 4 queries x 32 synthetic 224x224 pages through the reference-signature pipeline
     (encode loop -> pickle shards -> retrieve -> TREC run -> metrics) vs the oracle's embeddings + numpy cosine top-5."""

@@ -390,6 +390,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ residual prefetcher
+        // The fp32 residual stream (604 MB per ViT layer at 128 pages) never survives in L2 between kernels, and the
+        // epilogue warps can only keep ~4 KB each in flight, so their residual reads were DRAM-latency bound. This warp
+        // pulls tile i's residual rows into L2 while tile i's main loop runs, one tile ahead of the epilogue.
+        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.epi.resid != nullptr && (g.epi.ldo & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(g.epi.resid) & 15) == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                if (it > 0) mbar_wait(&tfull_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);  // main loop of tile it-1 is done
+                const int m0 = (t / tiles_n) * GEMM_BM;
+                const int n0 = (t % tiles_n) * BN;
+                const int cols = min(BN, g.N - n0) & ~3;  // bulk prefetch sizes are multiples of 16 bytes
+                if (cols == 0) continue;
+#pragma unroll
+                for (int r = lane; r < GEMM_BM; r += 32) {
+                    if (m0 + r < g.M)
+                        l2_prefetch_bulk(g.epi.resid + static_cast<int64_t>(m0 + r) * g.epi.ldo + n0, cols * 4);
+                }
+            }
+        }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
         const int ew = warp - 4;

@@ -3,8 +3,8 @@
   * `distributed_parallel_embedding_inference(dataset, model, args, dataset_type, split_save, model_additional_args)`
     == `src/openmatch/inference/inference.py:53-172`: batches of `{id,text,image}` -> `model(passage=|query=...)` ->
     pickle shards `embeddings.{corpus|query}.rank.{r}[.{a}-{b}]` = `pickle((float32[n,d], List[str]))`, barrier.
-    The per-batch blocking `.cpu()` of the reference (`:98`) is replaced by a pinned, double-buffered async device->host
-    copy: batch i's embeddings travel while batch i+1 is being encoded.
+    Built on `encode_stream`: host preparation of batch i+1, kernels of batch i and the device->host copy of batch i-1
+    overlap (the reference blocks on `.cpu()` every batch, `:98`).
   * `save_as_trec` / `load_from_trec` == `src/openmatch/utils.py:125-175` (same 6-column tab format).
   * `eval_mrr` == `utils.py:285-308`; `recall_at_k`, `ndcg_at_k` reproduce pytrec_eval's `recall.k` / `ndcg_cut.k`
     (`driver/eval.py:281-283`; pytrec_eval is not installed here): ranking by score descending, ties by doc id descending
@@ -45,50 +45,71 @@ def _dump(output_dir: str, name: str, encoded: List[np.ndarray], lookup: List[st
 
 
 @torch.no_grad()
+def encode_stream(batches: Iterable[dict], model, model_additional_args: Optional[dict] = None):
+    """Pipelined encode: yields (ids, float32 ndarray [n, d]) per batch, in order.
+
+    Three things overlap: the host preparation of batch i+1 (PIL resampling, tokenisation; worker thread), the kernels
+    of batch i (asynchronous launches on the current stream) and the device->host copy of batch i-1 (pinned buffer +
+    event instead of the reference's blocking `.cpu()`, `inference.py:98`)."""
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+
+    kw = model_additional_args or {}
+    it = iter(batches)
+    first = next(it, None)
+    if first is None:
+        return
+    pending = deque()
+
+    def collect():
+        ids, host, ev = pending.popleft()
+        ev.synchronize()
+        return ids, host.numpy().copy()
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        fut = pool.submit(model.prepare, first, **kw)
+        cur = first
+        while cur is not None:
+            pb = fut.result()
+            nxt = next(it, None)
+            if nxt is not None:
+                fut = pool.submit(model.prepare, nxt, **kw)
+            reps = model.encode_prepared(pb)
+            host = torch.empty(reps.shape, dtype=torch.float32).pin_memory()
+            host.copy_(reps, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((cur["id"], host, ev))
+            if len(pending) > 1:
+                yield collect()
+            cur = nxt
+    while pending:
+        yield collect()
+
+
+@torch.no_grad()
 def distributed_parallel_embedding_inference(dataset, model, args, dataset_type: str = "corpus", split_save: bool = True,
                                              model_additional_args: Optional[dict] = None) -> None:
     if dataset is None:
         raise ValueError("No dataset provided")
     if dataset_type not in ("corpus", "query"):
         raise ValueError(f"dataset_type: {dataset_type} is not valid.")
-    kw = model_additional_args or {}
     os.makedirs(args.output_dir, exist_ok=True)
     world = max(1, getattr(args, "world_size", 1))
     encoded: List[np.ndarray] = []
     lookup: List[str] = []
     idx = prev_idx = 0
-    pending = None  # (pinned host tensor, event): the previous batch's embeddings in flight to the host
     first = True
-
-    def collect():
-        nonlocal pending, first
-        if pending is None:
-            return
-        host, ev = pending
-        ev.synchronize()
-        arr = host.numpy().copy()
+    for ids, arr in encode_stream(_batches(dataset, args.per_device_eval_batch_size), model, model_additional_args):
         if first:
             assert not np.isnan(arr).any(), "vital error, model output has nan, please check."  # `inference.py:105-108`
             first = False
         encoded.append(arr)
-        pending = None
-
-    for batch in _batches(dataset, args.per_device_eval_batch_size):
-        out = model(passage=batch, **kw) if dataset_type == "corpus" else model(query=batch, **kw)
-        reps = out.p_reps if dataset_type == "corpus" else out.q_reps
-        collect()  # previous batch has certainly landed by now; keeps `encoded` in order
-        host = torch.empty(reps.shape, dtype=torch.float32).pin_memory()
-        host.copy_(reps, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        pending = (host, ev)
-        lookup.extend(batch["id"])
-        idx += len(batch["id"])
+        lookup.extend(ids)
+        idx += len(ids)
         if split_save and len(lookup) >= args.max_inmem_docs // world:
-            collect()
             _dump(args.output_dir, f"embeddings.{dataset_type}.rank.{args.process_index}.{prev_idx}-{idx}", encoded, lookup)
             encoded, lookup, prev_idx = [], [], idx
-    collect()
     if split_save:
         if lookup:
             _dump(args.output_dir, f"embeddings.{dataset_type}.rank.{args.process_index}.{prev_idx}-{idx}", encoded, lookup)

@@ -155,11 +155,19 @@ class DRModelForInference:
         if self.pooling not in ops.POOLING:
             raise ValueError("Unknown pooling type: {}".format(self.pooling))
         if isinstance(model, VisRAGRetB200):
-            tokenizer = kwargs["tokenizer"]
-            pb = prepare_batch(items["text"], items["image"], tokenizer, model.config, kwargs.get("max_inp_length", 2048))
-            return None, model.engine.encode_prepared(pb, self.pooling, True)
+            return None, self.encode_prepared(self.prepare(items, **kwargs))
         raise TypeError("DRModelForInference (visrag_b200) only drives a VisRAGRetB200 backbone: there is no "
                         "PyTorch/CPU fallback path in this package")
+
+    # The two halves of encode(): host preparation (CPU only, thread safe) and the device part (asynchronous launches).
+    # `inference.encode_stream` runs prepare() for batch i+1 on a worker thread while batch i is on the GPU.
+    def prepare(self, items, **kwargs):
+        return prepare_batch(items["text"], items["image"], kwargs["tokenizer"], self.lm_q.config, kwargs.get("max_inp_length", 2048))
+
+    @torch.no_grad()
+    def encode_prepared(self, pb):
+        assert self.normalize is True, "Normalize must be true"
+        return self.lm_q.engine.encode_prepared(pb, self.pooling, True)
 
     def encode_passage(self, psg, **kwargs):
         return self.encode(psg, self.lm_q, self.head_p, is_query=False, **kwargs)
