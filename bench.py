@@ -187,11 +187,13 @@ def run_ours(a):
         pass
     barrier()
     e0.record()
+    marks = [time.perf_counter()]
     for _, host_np in encode_stream([stream_items] * a.steps, model, kw):
-        pass
+        marks.append(time.perf_counter())  # batch i's embeddings are on the host
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    intervals = [round((b - a_) * 1e3, 1) for a_, b in zip(marks, marks[1:])]  # first one includes the pipeline fill
     e2e_value = world * a.steps * P / (e2e_ms / 1e3)
     host_reps = torch.from_numpy(host_np)
     e0.record()
@@ -293,7 +295,7 @@ def run_ours(a):
                        "lm_tokens_per_page": lm_tokens, "parallelism": f"dp{world} (pages sharded, no encode collective)",
                        "weights": "random-init, bf16", "l2": "working set (6.3 GB weights + >1 GB activations per step) >> 126 MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms / a.steps, 3),
+                    "ms_per_step": round(e2e_ms / a.steps, 3), "batch_intervals_ms": intervals,
                     "api": "inference.encode_stream (loop body of distributed_parallel_embedding_inference) over DRModelForInference",
                     "blocking": {"value": round(blocking_value, 2), "ms_per_step": round(blocking_ms / a.steps, 3),
                                  "api": "DRModelForInference.forward(passage=..., tokenizer=...).p_reps.cpu() per step"}},

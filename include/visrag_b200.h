@@ -68,6 +68,37 @@ typedef struct {
 int vr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_dtype, int32_t M, int32_t N, int32_t K,
             const vr_gemm_epilogue* epi, void* stream);
 
+/* Same operation with the kernel variant chosen by the caller (benchmarks, parity tests of every variant):
+ *   block_n = 0    what vr_gemm picks: 128x256 token-major tiles; 128(features)x256(tokens) feature-major tiles when
+ *                  N = 128 (mod 256), K >= 2048, M >= 4096 and the epilogue is LINEAR (no half-empty last tile)
+ *   block_n = 256 / 128   token-major accumulator, 128 tokens x block_n features per tile
+ *   block_n = 3    feature-major accumulator (the weight tile is the MMA's M operand), LINEAR epilogues only; its
+ *                  epilogue needs no shared-memory transpose
+ *   block_n = 2    CTA-pair kernel (tcgen05 cta_group::2, 256x256 tile per pair); correct, currently slower */
+int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_dtype, int32_t M, int32_t N,
+                  int32_t K, const vr_gemm_epilogue* epi, int32_t block_n, void* stream);
+
+
+/* ------------------------------------------------------------------------------------
+ * Device image front-end: Pillow-bit-compatible 8-bit bicubic resampling + grid crop.
+ * Replaces the host-side `image.resize(size, Image.BICUBIC)` calls of slice_image
+ * (modeling_minicpmv/modeling_minicpmv.py:509,519,531) and split_to_patches (:571-592); the arithmetic is
+ * Pillow's ImagingResample (src/libImaging/Resample.c): horizontal pass over source rows
+ * [row_first, row_first+row_count) into an 8-bit intermediate, then the vertical pass, 22-bit fixed-point
+ * coefficients, 32-bit sums, clip8. Results are bit-identical to PIL.
+ *   src        [n, in_h, in_w, 3] uint8 (n pages of one size)
+ *   bounds_*   [out, 2] int32 (first source index, tap count), coeffs_* [out, ksize_*] int32 fixed point, as
+ *              Pillow's precompute_coeffs + normalize_coeffs_8bpc produce them (frontend.resample_coeffs);
+ *              NULL for an axis whose size does not change (Pillow skips that pass)
+ *   tmp        workspace [n, row_count, out_w, 3] uint8, needed when both passes run
+ *   out        slice buffer [*, cell_h, cell_w, 3] uint8: the out_h x out_w result of page i is cut into
+ *              (out_h/cell_h) x (out_w/cell_w) cells, row-major, stored as slices first_cell[i], first_cell[i]+1, ...
+ *              (cell = whole image for the thumbnail). first_cell: [n] int32, device.
+ * ---------------------------------------------------------------------------------- */
+int vr_resample_u8(const uint8_t* src, int32_t n, int32_t in_h, int32_t in_w, const int32_t* bounds_h,
+                   const int32_t* coeffs_h, int32_t ksize_h, const int32_t* bounds_v, const int32_t* coeffs_v,
+                   int32_t ksize_v, int32_t row_first, int32_t row_count, int32_t out_h, int32_t out_w, uint8_t* tmp,
+                   uint8_t* out, const int32_t* first_cell, int32_t cell_h, int32_t cell_w, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused softmax(Q K^T * scale) V on tcgen05 (S and the P.V partial product live in TMEM,

@@ -82,6 +82,16 @@ def case_epilogues(bn):
     b2 = torch.randn(N2, device="cuda")
     got = ops.gemm(a, w2, bias=b2, gelu=True, block_n=bn)
     ok &= report("fc1-like N=4304 gelu", got, ref_linear(a, w2, b2, gelu=True), 1e-2)
+    # row-tail / odd token counts with a bf16 output (the feature-major kernel pairs lanes for its bf16 stores)
+    for M3 in (1, 31, 130):
+        a4 = a[:M3].contiguous()
+        got = ops.gemm(a4, w, bias=bias, block_n=bn)
+        ok &= report(f"bias bf16 M={M3}", got, ref_linear(a4, w, bias), 1e-2)
+        x = resid[:M3].clone()
+        got = ops.gemm(a4, w, resid=x, out=x, out_dtype=torch.float32, block_n=bn)
+        ok &= report(f"resid in-place f32 M={M3}", got, ref_linear(a4, w, resid=resid[:M3]), 2e-3)
+    if bn == 3:
+        return ok  # the feature-major kernel implements LINEAR epilogues only
     # RoPE epilogue
     T, H = 300, 2304
     hd = 64
@@ -112,13 +122,25 @@ def case_epilogues(bn):
     return ok
 
 
-def case_perf(bn):
+ANATOMY = [  # the epilogue-heavy ViT / LM shapes with the epilogue peeled off piece by piece
+    (131072, 1152, 4304, {}), (131072, 1152, 4304, {"f32": True}), (131072, 1152, 4304, {"resid": True}),
+    (131072, 1152, 1152, {}), (131072, 1152, 1152, {"f32": True}), (131072, 1152, 1152, {"resid": True}),
+    (131072, 4304, 1152, {}), (131072, 4304, 1152, {"gelu": True, "bias": True}),
+    (8704, 2304, 5760, {}), (8704, 2304, 5760, {"resid": True}), (8704, 2304, 2304, {}), (8704, 2304, 2304, {"resid": True}),
+]
+
+
+def case_anatomy(bn):
+    return case_perf(bn, ANATOMY, cublas=False)
+
+
+def case_perf(bn, shapes=None, cublas=True):
     import torch
     from visrag_b200 import ops
 
     torch.manual_seed(2)
     ok = True
-    for (M, N, K, kw) in [
+    for (M, N, K, kw) in shapes or [
         (65536, 3840, 1152, {}),
         (65536, 4304, 1152, {"gelu": True, "bias": True}),
         (65536, 1152, 4304, {"resid": True, "bias": True}),
@@ -134,6 +156,8 @@ def case_perf(bn):
         args = dict(bias=bias, gelu=kw.get("gelu", False), block_n=bn)
         if x is not None:
             args.update(resid=x, out=x, out_dtype=torch.float32)
+        elif kw.get("f32"):
+            args.update(out_dtype=torch.float32)
         for _ in range(3):
             ops.gemm(a, w, **args)
         torch.cuda.synchronize()
@@ -146,6 +170,9 @@ def case_perf(bn):
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / n
         tf = 2.0 * M * N * K / ms / 1e9
+        if not cublas:
+            print(f"perf bn={bn} M={M} N={N} K={K} {kw}: {ms:.3f} ms {tf:.1f} TFLOP/s", flush=True)
+            continue
         # cuBLAS for context
         for _ in range(3):
             torch.matmul(a, w.t())
@@ -160,7 +187,7 @@ def case_perf(bn):
     return ok
 
 
-CASES = {"basic": case_basic, "epilogues": case_epilogues, "perf": case_perf}
+CASES = {"basic": case_basic, "epilogues": case_epilogues, "perf": case_perf, "anatomy": case_anatomy}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3:
@@ -170,7 +197,7 @@ if __name__ == "__main__":
     log = open("gpurun_out/check_gemm.log", "w")
     rc_all = 0
     for case in ("basic", "epilogues", "perf"):
-        for bn in (256, 128):
+        for bn in (256, 128, 3):
             t0 = time.time()
             p = subprocess.run([sys.executable, __file__, case, str(bn)], capture_output=True, text=True, timeout=600)
             msg = f"=== {case} bn={bn} rc={p.returncode} ({time.time()-t0:.1f}s)\n{p.stdout}{p.stderr[-3000:]}\n"

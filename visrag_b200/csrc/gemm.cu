@@ -4,20 +4,23 @@
 
 namespace vr {
 
-template <int BN, int MODE, bool OUT_F32, bool GELU, int AB_FMT>
+template <int BN, int MODE, bool OUT_F32, bool GELU, int AB_FMT, bool SWAP = false>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     CUtensorMap ta, tb;
     const bool bf16 = AB_FMT == 1;
-    if (int rc = make_tmap_2d(&ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, bf16)) return rc;
-    if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, bf16)) return rc;
-    auto kern = gemm_tcgen05_kernel<BN, MODE, OUT_F32, GELU, AB_FMT>;
+    // both operands use 128-row x 64-column boxes, so the maps are interchangeable: SWAP hands the weight to the MMA's
+    // M side (128 features per tile) and the activations to its N side (BN tokens per tile)
+    if (int rc = make_tmap_2d(SWAP ? &tb : &ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, bf16)) return rc;
+    if (int rc = make_tmap_2d(SWAP ? &ta : &tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, bf16)) return rc;
+    auto kern = gemm_tcgen05_kernel<BN, MODE, OUT_F32, GELU, AB_FMT, SWAP>;
     static bool attr_set = false;  // per template instantiation
     if (!attr_set) {
         VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
+    const int tiles = SWAP ? ((g.N + GEMM_BM - 1) / GEMM_BM) * ((g.M + BN - 1) / BN)
+                           : ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
     VR_CHECK_CUDA(cudaGetLastError());
@@ -69,6 +72,19 @@ static int dispatch_mode2(const void* A, int64_t lda, const void* B, int64_t ldb
     }
 }
 
+// feature-major accumulator kernels (block_n == 3): LINEAR epilogues only
+static int dispatch_swapped(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s) {
+    const vr_gemm_epilogue& e = g.epi;
+    VR_REQUIRE(e.mode == VR_EPI_LINEAR, "vr_gemm: block_n=3 (feature-major accumulator) supports LINEAR epilogues only");
+    if (e.out_dtype == VR_F32) {
+        VR_REQUIRE(!e.act_gelu, "vr_gemm: GELU epilogue writes bf16 only");
+        return launch_gemm<256, VR_EPI_LINEAR, true, false, 1, true>(A, lda, B, ldb, g, s);
+    }
+    VR_REQUIRE(e.out_dtype == VR_BF16, "vr_gemm: out_dtype must be VR_BF16 or VR_F32");
+    if (e.act_gelu) return launch_gemm<256, VR_EPI_LINEAR, false, true, 1, true>(A, lda, B, ldb, g, s);
+    return launch_gemm<256, VR_EPI_LINEAR, false, false, 1, true>(A, lda, B, ldb, g, s);
+}
+
 template <int BN>
 static int dispatch_mode(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s) {
     const vr_gemm_epilogue& e = g.epi;
@@ -111,11 +127,18 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
     g.M = M; g.N = N; g.K = K; g.epi = *epi;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int bn = block_n;
-    if (bn == 0) bn = (N >= 256) ? 256 : 128;
+    if (bn == 0) {
+        bn = (N >= 256) ? 256 : 128;
+        // N = 128 (mod 256) wastes half of the last 256-wide tile (ViT fc2 / proj: N = 1152 -> 10 %). The feature-major
+        // kernel tiles N by 128 with full-rate M=128 x N=256 MMAs; measured faster when the main loop is long enough
+        // to hide its narrower (512-byte) residual rows: fc2 1140 vs 1094 TFLOP/s, proj (K = 1152) 765 vs 954.
+        if (epi->mode == VR_EPI_LINEAR && N % 256 == 128 && K >= 2048 && M >= 4096) bn = 3;
+    }
     if (bn == 2) return dispatch_mode2(A, lda, B, ldb, g, s);
+    if (bn == 3) return dispatch_swapped(A, lda, B, ldb, g, s);
     if (bn == 256) return dispatch_mode<256>(A, lda, B, ldb, g, s);
     if (bn == 128) return dispatch_mode<128>(A, lda, B, ldb, g, s);
-    set_error("vr_gemm: block_n must be 0 (auto), 128, 256 or 2 (CTA-pair kernel)");
+    set_error("vr_gemm: block_n must be 0 (auto), 128, 256, 2 (CTA-pair kernel) or 3 (feature-major accumulator)");
     return 2;
 }
 

@@ -228,6 +228,71 @@ __device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int l
     __syncwarp();
 }
 
+// LINEAR, feature-major accumulator (SWAP kernels: the WEIGHT tile is the MMA's M operand, 256 tokens are its N).
+// tcgen05.ld then hands every thread one output FEATURE and 32 consecutive tokens, which is already the shape global
+// memory wants: for a fixed token the 32 lanes hold 32 consecutive features = one 128-byte (fp32) row segment. No
+// shared-memory transpose, bias is a per-thread scalar, the residual comes in with the same coalesced pattern.
+template <bool OUT_F32, bool GELU>
+__device__ __forceinline__ void epi_linear_t(const GemmArgs& g, int lane, int f0, int tok0, float (&x)[32]) {
+    const vr_gemm_epilogue& e = g.epi;
+    const int toks = g.M - tok0;                 // may exceed 32
+    if (toks <= 0 || f0 >= g.N) return;          // warp-uniform
+    const int f = f0 + lane;
+    const bool fv = f < g.N;
+    float r[32];
+    if (e.resid) {
+        // all residual loads first (independent, one 128-byte segment per warp instruction)
+        const float* rp = e.resid + static_cast<long long>(tok0) * e.ldo + f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = (fv && j < toks) ? rp[static_cast<long long>(j) * e.ldo] : 0.0f;
+    }
+    if (e.bias) {
+        const float b = fv ? e.bias[f] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] += b;
+    }
+    if (GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) gelu_erf2(x[j], x[j + 1]);
+    }
+    if (e.scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] *= e.scale;
+    }
+    if (e.rowadd) {
+        int pr = tok0 % e.rowadd_period;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (fv && j < toks) x[j] += e.rowadd[static_cast<long long>(pr) * g.N + f];
+            if (++pr == e.rowadd_period) pr = 0;
+        }
+    }
+    if (e.resid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] += r[j];
+    }
+    if (OUT_F32) {
+        float* op = reinterpret_cast<float*>(e.out) + static_cast<long long>(tok0) * e.ldo + f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (fv && j < toks) op[static_cast<long long>(j) * e.ldo] = x[j];
+    } else {
+        // lanes 2i / 2i+1 hold features f, f+1: the even lane takes token j, the odd lane token j+1, each storing one
+        // packed bf16x2 (features f..f+1) -> two 64-byte row segments per warp store
+        const bool odd = lane & 1;
+        uint32_t* ob = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (f & ~1));
+        const bool pv = fv;                      // N is even: both features of the pair are valid or neither
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float send = odd ? x[j] : x[j + 1];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const uint32_t w = odd ? pack_bf16x2(recv, x[j + 1]) : pack_bf16x2(x[j], recv);
+            const int jj = j + (odd ? 1 : 0);
+            if (pv && jj < toks) ob[(static_cast<long long>(tok0 + jj) * e.ldo) >> 1] = w;
+        }
+    }
+}
+
 // RoPE (modeling_minicpm.py:259-290): a head is 64 columns [lo(32) | hi(32)];
 //   lo' = lo*cos - hi*sin ; hi' = hi*cos + lo*sin   with cos/sin[pos, 0..31].  Writes 64 bf16 columns.
 __device__ __forceinline__ void epi_rope(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&lo)[32],
@@ -281,7 +346,10 @@ __device__ __forceinline__ void epi_swiglu(const GemmArgs& g, uint8_t* st, int l
 }
 
 // ---------------------------------------------------------------------------------------
-template <int BN, int MODE, bool OUT_F32, bool GELU, int AB_FMT /*0 f16, 1 bf16*/>
+// SWAP = true (LINEAR only): the host passes the WEIGHT map as tmap_a and the activation map as tmap_b; accumulator
+// rows are output features (128 per tile), accumulator columns are tokens (BN per tile). g keeps its meaning
+// (M tokens, N features). Feature blocks vary fastest so that co-running CTAs share one activation tile in L2.
+template <int BN, int MODE, bool OUT_F32, bool GELU, int AB_FMT /*0 f16, 1 bf16*/, bool SWAP = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmArgs g) {
@@ -299,14 +367,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* tfull_bar = bars + 2 * STAGES;
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    volatile uint32_t* progress = tmem_slot + 1;  // tiles whose main loop has started (written by the MMA warp)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
-    const int tiles_n = (g.N + BN - 1) / BN;
+    static_assert(!SWAP || MODE == VR_EPI_LINEAR, "feature-major accumulators are implemented for LINEAR epilogues");
+    const int tiles_m = ((SWAP ? g.N : g.M) + GEMM_BM - 1) / GEMM_BM;
+    const int tiles_n = ((SWAP ? g.M : g.N) + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
+    // tile -> (first accumulator row, first accumulator column)
+    auto tile_m0 = [&](int t) { return (SWAP ? t % tiles_m : t / tiles_n) * GEMM_BM; };
+    auto tile_n0 = [&](int t) { return (SWAP ? t / tiles_m : t % tiles_n) * BN; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -321,6 +394,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
         }
+        *progress = 0;
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -335,8 +409,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / tiles_n) * GEMM_BM;
-                const int n0 = (t % tiles_n) * BN;
+                const int m0 = tile_m0(t);
+                const int n0 = tile_n0(t);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -371,6 +445,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
+            if (lane == 0) *progress = static_cast<uint32_t>(it + 1);  // main loop of tile `it` starts (prefetcher pacing)
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
@@ -394,20 +469,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ------------------------------------------------------------ residual prefetcher
         // The fp32 residual stream (604 MB per ViT layer at 128 pages) never survives in L2 between kernels, and the
         // epilogue warps can only keep ~4 KB each in flight, so their residual reads were DRAM-latency bound. This warp
-        // pulls tile i's residual rows into L2 while tile i's main loop runs, one tile ahead of the epilogue.
+        // pulls tile i's residual rows into L2 while tile i's main loop runs, one tile ahead of the epilogue. Pacing is
+        // a monotonic counter published by the MMA warp (not an mbarrier phase: a phase can be missed by a late
+        // waiter, a counter cannot), and a tile whose main loop is already over is skipped.
         if (MODE == VR_EPI_LINEAR && OUT_F32 && g.epi.resid != nullptr && (g.epi.ldo & 3) == 0 &&
             (reinterpret_cast<uintptr_t>(g.epi.resid) & 15) == 0) {
             int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                if (it > 0) mbar_wait(&tfull_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);  // main loop of tile it-1 is done
-                const int m0 = (t / tiles_n) * GEMM_BM;
-                const int n0 = (t % tiles_n) * BN;
-                const int cols = min(BN, g.N - n0) & ~3;  // bulk prefetch sizes are multiples of 16 bytes
+                uint32_t started;
+                while ((started = *progress) < static_cast<uint32_t>(it + 1)) __nanosleep(256);
+                if (started > static_cast<uint32_t>(it + 1)) continue;  // too late to be useful
+                const int tok0 = SWAP ? tile_n0(t) : tile_m0(t);
+                const int f0 = SWAP ? tile_m0(t) : tile_n0(t);
+                constexpr int TOKS = SWAP ? BN : GEMM_BM, FEATS = SWAP ? GEMM_BM : BN;
+                const int cols = min(FEATS, g.N - f0) & ~3;  // bulk prefetch sizes are multiples of 16 bytes
                 if (cols == 0) continue;
 #pragma unroll
-                for (int r = lane; r < GEMM_BM; r += 32) {
-                    if (m0 + r < g.M)
-                        l2_prefetch_bulk(g.epi.resid + static_cast<int64_t>(m0 + r) * g.epi.ldo + n0, cols * 4);
+                for (int r = lane; r < TOKS; r += 32) {
+                    if (tok0 + r < g.M)
+                        l2_prefetch_bulk(g.epi.resid + static_cast<int64_t>(tok0 + r) * g.epi.ldo + f0, cols * 4);
                 }
             }
         }
@@ -421,8 +501,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (t / tiles_n) * GEMM_BM;
-            const int n0 = (t % tiles_n) * BN;
+            const int m0 = tile_m0(t);
+            const int n0 = tile_n0(t);
             const int row0 = m0 + quarter * 32;  // first of this warp's 32 rows
             uint8_t* st = smem_stage + ew * Cfg::EPI_STAGE_BYTES;
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -443,7 +523,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
+                    if (SWAP) epi_linear_t<OUT_F32, GELU>(g, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
+                    else epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
                 }
             } else {
 #pragma unroll 1

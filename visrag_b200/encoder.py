@@ -38,10 +38,13 @@ class VisRAGEngine:
     """Holds device weights in kernel-ready layouts and runs the encode pipeline."""
 
     def __init__(self, cfg: VisRAGConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
-                 max_vit_tokens: int = 131072):
+                 max_vit_tokens: int = 131072, device_frontend: bool = False):
         cfg.validate()
         L.lib()  # fail loudly if the CUDA library is missing
         self.cfg = cfg
+        # True: pages travel as raw RGB and are resampled / cut into slices on the GPU (bit-identical to PIL,
+        # frontend.py); False: PIL renders the slices on the host as the reference does
+        self.device_frontend = device_frontend
         self.device = torch.device(device)
         self.max_vit_tokens = max_vit_tokens
         sd, dev = state_dict, self.device
@@ -217,42 +220,87 @@ class VisRAGEngine:
         return h
 
     # ------------------------------------------------------------------------------------------ end to end
-    def _stage(self, a: np.ndarray, key) -> torch.Tensor:
-        """numpy -> device through a persistent (grow-only) pinned staging buffer identified by `key`."""
-        t = torch.from_numpy(np.ascontiguousarray(a))
+    def _pinned_buf(self, key, n: int, dtype) -> torch.Tensor:
+        """Persistent (grow-only) pinned staging buffer identified by `key`."""
         buf = self._pinned.get(key)
-        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
-            buf = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1), dtype=dtype).pin_memory()
             self._pinned[key] = buf
-        stage = buf[: t.numel()].view(t.shape)
+        return buf[:n]
+
+    def _stage(self, a: np.ndarray, key) -> torch.Tensor:
+        """numpy -> device through pinned staging; the copy is enqueued on the CURRENT stream (the caller selects it)."""
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        stage = self._pinned_buf(key, t.numel(), t.dtype).view(t.shape)
         stage.copy_(t)
         return stage.to(self.device, non_blocking=True)
 
     def _stage_slices(self, slices, key) -> torch.Tensor:
         """List of S uint8 [h,w,3] arrays -> device [S,h,w,3], copied slice by slice into the pinned staging buffer."""
         h, w, c = slices[0].shape
-        n = len(slices) * h * w * c
-        buf = self._pinned.get(key)
-        if buf is None or buf.numel() < n:
-            buf = torch.empty(n, dtype=torch.uint8).pin_memory()
-            self._pinned[key] = buf
-        stage = buf[:n].view(len(slices), h, w, c)
+        stage = self._pinned_buf(key, len(slices) * h * w * c, torch.uint8).view(len(slices), h, w, c)
         dst = stage.numpy()
         for j, a in enumerate(slices):
             dst[j] = a
         return stage.to(self.device, non_blocking=True)
 
+    def _upload_group(self, key, slices, s: int) -> torch.Tensor:
+        """One geometry group -> device [S,h,w,3]; entries rendered by the device front-end (None) are left to it."""
+        host = [i for i, a in enumerate(slices) if a is not None]
+        if len(host) == len(slices):
+            return self._stage_slices(slices, (s, "px", key))
+        dev = torch.empty((len(slices), key[0], key[1], 3), dtype=torch.uint8, device=self.device)
+        if host:
+            dev[torch.tensor(host, device=self.device)] = self._stage_slices([slices[i] for i in host], (s, "px", key))
+        return dev
+
+    def _render_jobs(self, jobs, groups, s: int) -> None:
+        """Device front-end: raw pages (stacked per page size) -> thumbnails and grid cells, written into `groups`."""
+        from .frontend import DeviceFrontEnd
+
+        if not hasattr(self, "_frontend"):
+            self._frontend = DeviceFrontEnd(self.device)
+        by_size = {}
+        for j in jobs:
+            by_size.setdefault(j.pixels.shape[:2], []).append(j)
+        for (H, W), lst in by_size.items():
+            pages = self._stage_slices([j.pixels for j in lst], (s, "page", (H, W)))
+            plan = lst[0].plan  # a function of (W, H) only
+            tkey = lst[0].thumb[0]
+            first = self._stage(np.asarray([j.thumb[1] for j in lst], dtype=np.int32), (s, "first_t", (H, W)))
+            self._frontend.resize_into(pages, plan.source_size[0], plan.source_size[1], groups[tkey], first,
+                                       plan.source_size[0], plan.source_size[1])
+            if plan.grid is not None:
+                ckey = lst[0].cells[0]
+                first = self._stage(np.asarray([j.cells[1] for j in lst], dtype=np.int32), (s, "first_c", (H, W)))
+                self._frontend.resize_into(pages, plan.refine_size[0], plan.refine_size[1], groups[ckey], first,
+                                           plan.cell_size[0], plan.cell_size[1])
+            pages.record_stream(torch.cuda.current_stream(self.device))
+
     def upload(self, pb: PreparedBatch):
-        """Host -> device copies of one prepared batch: pinned staging, async on the current stream. The staging
-        buffers are reused, so the previous upload's copies are waited for first (they finished long ago)."""
+        """Host -> device copies of one prepared batch. Pinned staging is double buffered and the copies run on a
+        dedicated copy stream, so batch i+1 travels over PCIe while batch i's kernels run; the compute stream only
+        waits on the copy's event. A staging set is reused every second upload, after its previous copy completed."""
         if not hasattr(self, "_pinned"):
-            self._pinned, self._upload_done = {}, None
-        if self._upload_done is not None:
-            self._upload_done.synchronize()
-        groups = {k: self._stage_slices(v, ("px", k)) for k, v in pb.groups.items()}
-        out = groups, self._stage(pb.token_src, "src"), self._stage(pb.positions, "pos"), self._stage(pb.cu_seqlens, "cu")
-        self._upload_done = torch.cuda.Event()
-        self._upload_done.record()
+            self._pinned, self._upload_done, self._flip = {}, [None, None], 0
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        s = self._flip
+        self._flip ^= 1
+        if self._upload_done[s] is not None:
+            self._upload_done[s].synchronize()
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            groups = {k: self._upload_group(k, v, s) for k, v in pb.groups.items()}
+            if pb.jobs:
+                self._render_jobs(pb.jobs, groups, s)
+            out = (groups, self._stage(pb.token_src, (s, "src")), self._stage(pb.positions, (s, "pos")),
+                   self._stage(pb.cu_seqlens, (s, "cu")))
+            ev = torch.cuda.Event()
+            ev.record()
+        self._upload_done[s] = ev
+        compute.wait_event(ev)
+        for t in (*groups.values(), *out[1:]):
+            t.record_stream(compute)  # allocated on the copy stream, consumed (and later freed) under the compute stream
         return out
 
     def encode_device(self, groups, group_row0, n_slices: int, src, pos, cu, max_len: int, pooling: str = "wmean",
@@ -276,5 +324,5 @@ class VisRAGEngine:
     def encode(self, texts: Sequence[str], images: Sequence, tokenizer, max_inp_length: Optional[int] = 2048,
                pooling: str = "wmean", normalize: bool = True) -> torch.Tensor:
         """(texts, PIL images | None) -> fp32 device tensor [B, hidden], L2-normalised."""
-        pb = prepare_batch(texts, images, tokenizer, self.cfg, max_inp_length)
+        pb = prepare_batch(texts, images, tokenizer, self.cfg, max_inp_length, self.device_frontend)
         return self.encode_prepared(pb, pooling, normalize)

@@ -144,6 +144,16 @@ def _tokenize(content: str, tokenizer, max_inp_length: Optional[int]) -> Tuple[n
 
 
 @dataclass
+class PageJob:
+    """A page whose slices the DEVICE front-end renders (frontend.DeviceFrontEnd): raw pixels + plan + where the
+    results go (group key, index inside the group) for the thumbnail and for the first grid cell."""
+    pixels: np.ndarray                                   # uint8 [H,W,3]
+    plan: SlicePlan
+    thumb: Optional[Tuple[Tuple[int, int], int]] = None
+    cells: Optional[Tuple[Tuple[int, int], int]] = None
+
+
+@dataclass
 class PreparedBatch:
     """Packed representation of a batch of (text, image) items."""
     n_items: int
@@ -151,20 +161,26 @@ class PreparedBatch:
     cu_seqlens: np.ndarray               # [B+1] int32
     positions: np.ndarray                # [T] int32, position inside the sequence
     token_src: np.ndarray                # [T] int32: >=0 row of the vision buffer; <0 -> -(token_id+1)
-    groups: Dict[Tuple[int, int], List[np.ndarray]] = field(default_factory=dict)   # (h,w) -> S uint8 [h,w,3] slices
+    # (h,w) -> S slices: uint8 [h,w,3] arrays rendered on the host, or None = rendered on the device by one of `jobs`
+    groups: Dict[Tuple[int, int], List[Optional[np.ndarray]]] = field(default_factory=dict)
     group_row0: Dict[Tuple[int, int], int] = field(default_factory=dict)      # (h,w) -> first slice index
     n_slices: int = 0
+    jobs: List[PageJob] = field(default_factory=list)
 
     def pixel_bytes(self) -> int:
-        return sum(a.nbytes for lst in self.groups.values() for a in lst)
+        """Pixel bytes that cross PCIe: host-rendered slices plus the raw pages of the device front-end."""
+        return (sum(a.nbytes for lst in self.groups.values() for a in lst if a is not None)
+                + sum(j.pixels.nbytes for j in self.jobs))
 
 
 def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAGConfig,
-                  max_inp_length: Optional[int] = 2048) -> PreparedBatch:
-    """Everything `VisRAG_Ret.forward` does before `get_vllm_embedding` (`modeling_visrag_ret.py:96-111`)."""
+                  max_inp_length: Optional[int] = 2048, device_frontend: bool = False) -> PreparedBatch:
+    """Everything `VisRAG_Ret.forward` does before `get_vllm_embedding` (`modeling_visrag_ret.py:96-111`).
+    With `device_frontend` the pages are not resampled here: their raw RGB pixels travel to the GPU and
+    `frontend.DeviceFrontEnd` renders the same slices there (bit-identical to PIL)."""
     if len(texts) != len(images):
         raise ValueError("texts and images must have the same length")
-    per_item_slices: List[List[np.ndarray]] = []
+    per_item_slices: list = []  # per item: list of host-rendered slices, or a PageJob
     ids_list, bound_list = [], []
     for text in texts:
         if not isinstance(text, str):
@@ -174,7 +190,11 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
         text, image = item
         if image:
             plan = plan_slices(image.size[0], image.size[1], cfg)
-            return render_slices(image, plan), placeholder_text(plan, tokenizer, cfg.query_num) + "\n" + text
+            content = placeholder_text(plan, tokenizer, cfg.query_num) + "\n" + text
+            if device_frontend:
+                rgb = image.convert("RGB") if image.mode != "RGB" else image
+                return PageJob(np.ascontiguousarray(_rgb_array(rgb)), plan), content
+            return render_slices(image, plan), content
         return [], text
 
     n_img = sum(1 for im in images if im)
@@ -185,8 +205,16 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
             prepared = list(ex.map(one, zip(texts, images)))
     else:
         prepared = [one(it) for it in zip(texts, images)]
-    for slices, content in prepared:
+    for (slices, content), image in zip(prepared, images):
         ids, bound = tokenize(content, tokenizer, max_inp_length)
+        if isinstance(slices, PageJob) and len(bound) != slices.plan.n_slices:
+            # truncated by max_inp_length (or stray markers): only some slices are consumed -> render on the host
+            slices = render_slices(image, slices.plan)
+        if isinstance(slices, PageJob):
+            per_item_slices.append(slices)
+            ids_list.append(ids)
+            bound_list.append(bound)
+            continue
         if len(bound) > len(slices):
             raise ValueError("more <image> spans in the text than slices")
         if any(int(e - s) != cfg.query_num for s, e in bound):
@@ -196,14 +224,23 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
         bound_list.append(bound)
 
     # group slices by geometry; every slice gets a global index = position in the vision output buffer / query_num
-    order: Dict[Tuple[int, int], List[np.ndarray]] = {}
+    order: Dict[Tuple[int, int], List[Optional[np.ndarray]]] = {}
     slot: List[List[Tuple[Tuple[int, int], int]]] = []
+    jobs: List[PageJob] = []
     for slices in per_item_slices:
         cur = []
-        for s in slices:
-            key = (s.shape[0], s.shape[1])
-            order.setdefault(key, []).append(s)
-            cur.append((key, len(order[key]) - 1))
+        if isinstance(slices, PageJob):
+            for n, (w, h) in enumerate(slices.plan.slice_sizes()):
+                order.setdefault((h, w), []).append(None)
+                cur.append(((h, w), len(order[(h, w)]) - 1))
+            slices.thumb = cur[0]
+            slices.cells = cur[1] if len(cur) > 1 else None
+            jobs.append(slices)
+        else:
+            for s in slices:
+                key = (s.shape[0], s.shape[1])
+                order.setdefault(key, []).append(s)
+                cur.append((key, len(order[key]) - 1))
         slot.append(cur)
     groups, row0, base = {}, {}, 0
     for key, lst in order.items():
@@ -223,4 +260,4 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
             key, j = slot[b][n]
             seg[s:e] = (row0[key] + j) * cfg.query_num + np.arange(e - s)
         src[cu[b]:cu[b + 1]] = seg.astype(np.int32)
-    return PreparedBatch(len(ids_list), seq_lens, cu, positions, src, groups, row0, base)
+    return PreparedBatch(len(ids_list), seq_lens, cu, positions, src, groups, row0, base, jobs)

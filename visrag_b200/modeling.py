@@ -105,7 +105,7 @@ class VisRAGRetB200:
             raise NotImplementedError("precomputed vision_hidden_states are not forwarded by the reference either "
                                       "(`modeling_visrag_ret.py:106-111`)")
         eng = self.engine
-        pb = prepare_batch(text, image, tokenizer, self.config, max_inp_length)
+        pb = prepare_batch(text, image, tokenizer, self.config, max_inp_length, eng.device_frontend)
         groups, src, pos, cu = eng.upload(pb)
         vision = eng.encode_vision(groups, pb.group_row0, pb.n_slices)
         h = eng.lm_hidden(src, pos, cu, int(pb.seq_lens.max()), vision)
@@ -162,7 +162,8 @@ class DRModelForInference:
     # The two halves of encode(): host preparation (CPU only, thread safe) and the device part (asynchronous launches).
     # `inference.encode_stream` runs prepare() for batch i+1 on a worker thread while batch i is on the GPU.
     def prepare(self, items, **kwargs):
-        return prepare_batch(items["text"], items["image"], kwargs["tokenizer"], self.lm_q.config, kwargs.get("max_inp_length", 2048))
+        return prepare_batch(items["text"], items["image"], kwargs["tokenizer"], self.lm_q.config,
+                             kwargs.get("max_inp_length", 2048), self.lm_q.engine.device_frontend)
 
     @torch.no_grad()
     def encode_prepared(self, pb):
