@@ -190,6 +190,11 @@ int vr_score_exact(const float* q_f32, int32_t nq, const float* d_f32, int64_t n
  * (negative ids are skipped): also the k-way merge of per-shard / per-rank partial top-k lists. */
 int vr_topk_rows(const float* scores, const int64_t* ids, int32_t rows, int64_t cols, int32_t k, int64_t id_offset,
                  float* out_scores, int64_t* out_ids, void* stream);
+/* Same result for few rows x many columns (single-query retrieval over a large index): `chunks` blocks per row each
+ * reduce a column range to a top-k list (pass 1, workspace ws_scores / ws_ids [rows, chunks, k]), then the lists are
+ * merged (pass 2). One block per row would scan a 1 M-column row k times on a single SM. */
+int vr_topk_rows_chunked(const float* scores, int32_t rows, int64_t cols, int32_t k, int64_t id_offset, int32_t chunks,
+                         float* ws_scores, int64_t* ws_ids, float* out_scores, int64_t* out_ids, void* stream);
 
 #ifdef __cplusplus
 }

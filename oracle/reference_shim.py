@@ -36,7 +36,7 @@ def _import_reference():
     sys.dont_write_bytecode = True
     for p in (os.path.join(REF_ROOT, "timm_modified"), os.path.join(REF_ROOT, "src")):
         if p not in sys.path:
-            sys.path.insert(0, p)
+            sys.path.append(p)  # at the END: the reference trees carry their own `tests` package, which must not shadow ours
     import transformers.utils.import_utils as iu
 
     if not hasattr(iu, "is_torch_fx_available"):

@@ -27,7 +27,7 @@ def _run(Q, D, k, **kw):
 
 
 @pytest.mark.parametrize("nq,nd,d,k", [(300, 5000, 256, 10), (1000, 10000, 2304, 10), (129, 4097, 2304, 5), (4, 32, 256, 5),
-                                       (2049, 20000, 64, 16), (1, 100000, 128, 10)])
+                                       (2049, 20000, 64, 16), (1, 100000, 128, 10), (3, 300000, 64, 12)])
 def test_topk_equals_fp32_scan(nq, nd, d, k):
     rs = np.random.RandomState(nq + nd)
     Q, D = _unit(rs, nq, d), _unit(rs, nd, d)
@@ -126,3 +126,32 @@ def test_merge_topk_kernel():
     ms, mi = R.merge_topk(torch.from_numpy(s).cuda(), torch.from_numpy(i).cuda(), 7)
     ws, wi = O.merge_topk([(s[:, :20], i[:, :20])], 7)
     assert np.array_equal(mi.cpu().numpy(), wi) and np.allclose(ms.cpu().numpy(), ws)
+
+
+def test_knowledge_base_single_query_retrieval(tmp_path):
+    """Demo layout (reps.npy + index2img_filename.txt): resident index, one query -> top-k page paths; equals the
+    fp32 scan the reference's answer.py does (torch.matmul + topk), ties by lower page index."""
+    from visrag_b200 import knowledge_base as KB
+
+    rs = np.random.RandomState(8)
+    D = _unit(rs, 50000, 256)
+    D[123] = D[77]                                  # an exact duplicate page -> a score tie
+    names = [f"doc.pdf_{i}.png" for i in range(len(D))]
+    KB.save_knowledge_base(str(tmp_path), D, names)
+    kb = KB.KnowledgeBase(str(tmp_path))
+    assert len(kb) == 50000
+    q = D[77:78] + 0.01 * _unit(rs, 1, 256)
+    q /= np.linalg.norm(q)
+    paths = kb.retrieve(q, 5)
+    s_ref, i_ref = O.score_topk(q.astype(np.float32), D, 5)
+    assert paths == [os.path.join(str(tmp_path), names[i]) for i in i_ref[0]]
+    assert i_ref[0][0] == 77 and i_ref[0][1] == 123
+    s, i = kb.search(q, 5)
+    assert np.abs(s.cpu().numpy() - s_ref).max() <= 2e-6
+    # several queries at once and k larger than the index
+    s, i = kb.search(D[:4], 3)
+    assert np.array_equal(i.cpu().numpy()[:, 0], np.arange(4))
+    small = KB.KnowledgeBase.__new__(KB.KnowledgeBase)
+    KB.save_knowledge_base(str(tmp_path / "s"), D[:3], names[:3])
+    small.__init__(str(tmp_path / "s"))
+    assert len(small.retrieve(D[:1], 10)) == 3

@@ -1,6 +1,8 @@
 """Run files + metrics (drop-ins for src/openmatch/utils.py and driver/eval.py:272-304). CPU only."""
 import math
 
+import numpy as np
+
 import pytest
 
 from visrag_b200 import inference as I
@@ -44,3 +46,17 @@ def test_collator_and_save_results(tmp_path):
     out = I.save_results(str(tmp_path), {"q": {"d": 1}}, {"q": {"d": 0.3, "e": 0.9}})
     assert out["recall_10"] == 1.0 and out["mrr_10"] == 0.5
     assert len(open(tmp_path / "test_result.log").read().splitlines()) == 3
+
+
+def test_knowledge_base_files_match_the_demo_layout(tmp_path):
+    """reps.npy + index2img_filename.txt exactly as visrag_pipeline/build_index.py:52-58 writes them."""
+    from visrag_b200 import knowledge_base as KB
+
+    reps = np.random.RandomState(0).randn(5, 8).astype(np.float32)
+    names = [f"doc.pdf_{i}.png" for i in range(5)]
+    KB.save_knowledge_base(str(tmp_path / "kb"), reps, names)
+    assert np.array_equal(np.load(tmp_path / "kb" / "reps.npy"), reps) and np.load(tmp_path / "kb" / "reps.npy").dtype == np.float32
+    assert (tmp_path / "kb" / "index2img_filename.txt").read_text() == "\n".join(names)   # no trailing newline
+    with pytest.raises(ValueError):
+        KB.save_knowledge_base(str(tmp_path / "kb2"), reps, names[:4])
+    assert KB.DEMO_QUERY_PREFIX.endswith("document: ")

@@ -360,19 +360,23 @@ exact_scores_kernel(const float* __restrict__ Q, int nq, const float* __restrict
 // top-k of each row of a dense [rows, cols] fp32 matrix (optionally with explicit ids per entry).
 __global__ void __launch_bounds__(256)
 topk_rows_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long cols, int k,
-                 long long id_offset, float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+                 long long id_offset, long long chunk_cols, float* __restrict__ out_scores,
+                 long long* __restrict__ out_ids) {
+    // block (row, chunk): top-k of columns [chunk*chunk_cols, ...) of one row, written as list `row*gridDim.y + chunk`
     __shared__ float red_s[8];
     __shared__ long long red_i[8];
-    const int row = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* srow = scores + static_cast<long long>(row) * cols;
-    const long long* irow = ids ? ids + static_cast<long long>(row) * cols : nullptr;
+    const long long c_lo = static_cast<long long>(blockIdx.y) * chunk_cols;
+    const long long c_hi = min(cols, c_lo + chunk_cols);
+    const float* srow = scores + static_cast<long long>(blockIdx.x) * cols;
+    const long long* irow = ids ? ids + static_cast<long long>(blockIdx.x) * cols : nullptr;
+    const long long row = static_cast<long long>(blockIdx.x) * gridDim.y + blockIdx.y;  // output list
     float last_s = INFINITY;
     long long last_i = -1;
     for (int round = 0; round < k; ++round) {
         float bs = -INFINITY;
         long long bi = 0x7fffffffffffffffll;
-        for (long long c = threadIdx.x; c < cols; c += 256) {
+        for (long long c = c_lo + threadIdx.x; c < c_hi; c += 256) {
             const long long id = irow ? irow[c] : c;
             if (id < 0) continue;
             const float s = srow[c];
@@ -393,13 +397,13 @@ topk_rows_kernel(const float* __restrict__ scores, const long long* __restrict__
         __syncthreads();
         const bool valid = bi != 0x7fffffffffffffffll;
         if (threadIdx.x == 0) {
-            out_scores[static_cast<long long>(row) * k + round] = valid ? bs : -INFINITY;
-            out_ids[static_cast<long long>(row) * k + round] = valid ? bi + id_offset : -1;
+            out_scores[row * k + round] = valid ? bs : -INFINITY;
+            out_ids[row * k + round] = valid ? bi + id_offset : -1;
         }
         if (!valid) {
             for (int r2 = round + 1 + threadIdx.x; r2 < k; r2 += 256) {
-                out_scores[static_cast<long long>(row) * k + r2] = -INFINITY;
-                out_ids[static_cast<long long>(row) * k + r2] = -1;
+                out_scores[row * k + r2] = -INFINITY;
+                out_ids[row * k + r2] = -1;
             }
             break;
         }
@@ -532,7 +536,27 @@ extern "C" int vr_topk_rows(const float* scores, const int64_t* ids, int32_t row
     VR_REQUIRE(scores && out_scores && out_ids, "vr_topk_rows: null pointer");
     VR_REQUIRE(rows > 0 && cols > 0 && k > 0, "vr_topk_rows: bad shape");
     topk_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        scores, reinterpret_cast<const long long*>(ids), cols, k, id_offset, out_scores, reinterpret_cast<long long*>(out_ids));
+        scores, reinterpret_cast<const long long*>(ids), cols, k, id_offset, cols, out_scores,
+        reinterpret_cast<long long*>(out_ids));
+    VR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vr_topk_rows_chunked(const float* scores, int32_t rows, int64_t cols, int32_t k, int64_t id_offset,
+                                    int32_t chunks, float* ws_scores, int64_t* ws_ids, float* out_scores,
+                                    int64_t* out_ids, void* stream) {
+    VR_REQUIRE(scores && ws_scores && ws_ids && out_scores && out_ids, "vr_topk_rows_chunked: null pointer");
+    VR_REQUIRE(rows > 0 && cols > 0 && k > 0 && chunks > 0 && chunks <= 65535, "vr_topk_rows_chunked: bad shape");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long long chunk_cols = (cols + chunks - 1) / chunks;
+    // pass 1: every (row, chunk) block reduces its column range to a sorted top-k list (ids = column + id_offset)
+    topk_rows_kernel<<<dim3(rows, chunks), 256, 0, s>>>(scores, nullptr, cols, k, id_offset, chunk_cols, ws_scores,
+                                                        reinterpret_cast<long long*>(ws_ids));
+    VR_CHECK_CUDA(cudaGetLastError());
+    // pass 2: merge the `chunks` lists of each row (explicit ids; exhausted lists carry id -1 and are skipped)
+    topk_rows_kernel<<<rows, 256, 0, s>>>(ws_scores, reinterpret_cast<const long long*>(ws_ids),
+                                          static_cast<long long>(chunks) * k, k, 0, static_cast<long long>(chunks) * k,
+                                          out_scores, reinterpret_cast<long long*>(out_ids));
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -38,7 +38,7 @@ class VisRAGEngine:
     """Holds device weights in kernel-ready layouts and runs the encode pipeline."""
 
     def __init__(self, cfg: VisRAGConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
-                 max_vit_tokens: int = 131072, device_frontend: bool = False):
+                 max_vit_tokens: int = 131072, device_frontend: bool = True):
         cfg.validate()
         L.lib()  # fail loudly if the CUDA library is missing
         self.cfg = cfg

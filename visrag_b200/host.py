@@ -143,6 +143,9 @@ def _tokenize(content: str, tokenizer, max_inp_length: Optional[int]) -> Tuple[n
     return ids, bound
 
 
+MAX_DEVICE_PAGE_WIDTH = 160 * 1024 // 3  # vr_resample_u8 stages one source row in shared memory
+
+
 @dataclass
 class PageJob:
     """A page whose slices the DEVICE front-end renders (frontend.DeviceFrontEnd): raw pixels + plan + where the
@@ -191,7 +194,9 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
         if image:
             plan = plan_slices(image.size[0], image.size[1], cfg)
             content = placeholder_text(plan, tokenizer, cfg.query_num) + "\n" + text
-            if device_frontend:
+            # a page that needs no resampling (already thumbnail sized, no grid) gains nothing from the device path
+            resampled = plan.grid is not None or tuple(image.size) != tuple(plan.source_size)
+            if device_frontend and resampled and image.size[0] <= MAX_DEVICE_PAGE_WIDTH:
                 rgb = image.convert("RGB") if image.mode != "RGB" else image
                 return PageJob(np.ascontiguousarray(_rgb_array(rgb)), plan), content
             return render_slices(image, plan), content

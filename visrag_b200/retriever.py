@@ -80,8 +80,15 @@ def _exact_topk(q: torch.Tensor, index: CorpusIndex, k: int, id_offset: int):
     for r0 in range(0, nq, rows_per):
         n = min(rows_per, nq - r0)
         L.check(lib.vr_score_exact(q[r0:].data_ptr(), n, index.emb.data_ptr(), nd, d, scratch.data_ptr(), L.stream_ptr()))
-        L.check(lib.vr_topk_rows(scratch.data_ptr(), None, n, nd, k, id_offset, out_s[r0:].data_ptr(), out_i[r0:].data_ptr(),
-                                 L.stream_ptr()))
+        chunks = min(1024, nd // 4096) if n <= 64 else 0  # few queries over a long index: spread each row over many SMs
+        if chunks >= 2:
+            ws_s = torch.empty((n, chunks, k), dtype=torch.float32, device=q.device)
+            ws_i = torch.empty((n, chunks, k), dtype=torch.int64, device=q.device)
+            L.check(lib.vr_topk_rows_chunked(scratch.data_ptr(), n, nd, k, id_offset, chunks, ws_s.data_ptr(), ws_i.data_ptr(),
+                                             out_s[r0:].data_ptr(), out_i[r0:].data_ptr(), L.stream_ptr()))
+        else:
+            L.check(lib.vr_topk_rows(scratch.data_ptr(), None, n, nd, k, id_offset, out_s[r0:].data_ptr(),
+                                     out_i[r0:].data_ptr(), L.stream_ptr()))
     return out_s, out_i
 
 
