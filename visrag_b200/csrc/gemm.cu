@@ -1,3 +1,5 @@
+#include <cstdio>
+#include <cstdlib>
 #include "common.h"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -40,7 +42,27 @@ static int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, 
         attr_set = true;
     }
     const int tiles = ((g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((g.N + Cfg::BN - 1) / Cfg::BN);
-    const int pairs = num_sms() / 2;
+    // A persistent kernel must not launch more clusters than can be co-resident: GPCs with an odd number of usable SMs
+    // cannot pair all of them, and a cluster that has to wait for a free pair would run its whole tile list after the
+    // others finished (measured: 74 clusters requested -> about half the throughput). Ask the driver.
+    static int max_pairs = 0;
+    if (max_pairs == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / 2 * 2);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        VR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        VR_REQUIRE(n > 0, "vr_gemm: the CTA-pair kernel cannot be scheduled on this device");
+        max_pairs = n;
+        if (getenv("VR_VERBOSE")) fprintf(stderr, "[visrag_b200] co-resident CTA pairs: %d of %d\n", n, num_sms() / 2);
+    }
+    const int pairs = max_pairs < num_sms() / 2 ? max_pairs : num_sms() / 2;
     const int clusters = tiles < pairs ? tiles : pairs;
     kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, g);
     VR_CHECK_CUDA(cudaGetLastError());
