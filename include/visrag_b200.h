@@ -69,12 +69,11 @@ int vr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_d
             const vr_gemm_epilogue* epi, void* stream);
 
 /* Same operation with the kernel variant chosen by the caller (benchmarks, parity tests of every variant):
- *   block_n = 0    what vr_gemm picks: 128x256 token-major tiles; 128(features)x256(tokens) feature-major tiles when
- *                  N = 128 (mod 256), K >= 2048, M >= 4096 and the epilogue is LINEAR (no half-empty last tile)
- *   block_n = 256 / 128   token-major accumulator, 128 tokens x block_n features per tile
- *   block_n = 3    feature-major accumulator (the weight tile is the MMA's M operand), LINEAR epilogues only; its
- *                  epilogue needs no shared-memory transpose
- *   block_n = 2    CTA-pair kernel (tcgen05 cta_group::2, 256x256 tile per pair); correct, currently slower */
+ *   block_n = 0    what vr_gemm picks: the CTA-pair kernel when M > 128 and N >= 256, else 128-row tiles
+ *   block_n = 2    CTA-pair kernel (tcgen05 cta_group::2, one 256x256 tile per pair of SMs, each CTA stages half of B)
+ *   block_n = 256 / 128   single-CTA kernel, token-major accumulator, 128 tokens x block_n features per tile
+ *   block_n = 3    single-CTA kernel, feature-major accumulator (the weight tile is the MMA's M operand), LINEAR
+ *                  epilogues only; its epilogue needs no shared-memory transpose */
 int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_dtype, int32_t M, int32_t N,
                   int32_t K, const vr_gemm_epilogue* epi, int32_t block_n, void* stream);
 

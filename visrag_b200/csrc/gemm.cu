@@ -150,11 +150,10 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int bn = block_n;
     if (bn == 0) {
-        bn = (N >= 256) ? 256 : 128;
-        // N = 128 (mod 256) wastes half of the last 256-wide tile (ViT fc2 / proj: N = 1152 -> 10 %). The feature-major
-        // kernel tiles N by 128 with full-rate M=128 x N=256 MMAs; measured faster when the main loop is long enough
-        // to hide its narrower (512-byte) residual rows: fc2 1140 vs 1094 TFLOP/s, proj (K = 1152) 765 vs 954.
-        if (epi->mode == VR_EPI_LINEAR && N % 256 == 128 && K >= 2048 && M >= 4096) bn = 3;
+        // CTA-pair kernel (tcgen05 cta_group::2) wherever a pair has a full 256-row tile to work on: each SM stages only
+        // half of B, which lifts the shared-memory/L2 feed limit of the single-CTA kernel (measured, in isolation: qkv
+        // 1585 vs 1334 TFLOP/s, fc2+resid 1290 vs 1094, LM down 1197 vs 1048). Small problems keep 128-row tiles.
+        bn = (M > 128 && N >= 256) ? 2 : (N >= 256 ? 256 : 128);
     }
     if (bn == 2) return dispatch_mode2(A, lda, B, ldb, g, s);
     if (bn == 3) return dispatch_swapped(A, lda, B, ldb, g, s);

@@ -42,6 +42,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint64_t* tfull_bar = bars + 2 * STAGES;
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    volatile uint32_t* progress = tmem_slot + 1;  // tiles whose main loop has started; the leader writes BOTH CTAs' copy
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -67,6 +68,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS);  // used in the leader only
         }
+        *progress = 0;
         fence_mbar_init();
     }
     cluster_sync_all();  // both CTAs resident and their barriers initialised before the pair-wide TMEM allocation
@@ -108,6 +110,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
+                if (lane == 0) {  // main loop of tile `it` starts: pace the residual prefetch warps of both CTAs
+                    *progress = static_cast<uint32_t>(it + 1);
+                    st_shared_cluster_u32(mapa_u32(smem_u32(const_cast<uint32_t*>(progress)), 1), static_cast<uint32_t>(it + 1));
+                }
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
@@ -124,6 +130,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ residual prefetcher (both CTAs, own 128 rows);
+        // see gemm.cuh: pulls tile i's fp32 residual rows into L2 while tile i's main loop runs
+        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.epi.resid != nullptr && (g.epi.ldo & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(g.epi.resid) & 15) == 0) {
+            int it = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                uint32_t started;
+                while ((started = *progress) < static_cast<uint32_t>(it + 1)) __nanosleep(256);
+                if (started > static_cast<uint32_t>(it + 1)) continue;  // too late to be useful
+                const int m0 = (t / tiles_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+                const int n0 = (t % tiles_n) * BN;
+                const int cols = min(BN, g.N - n0) & ~3;
+                if (cols <= 0) continue;
+#pragma unroll
+                for (int r = lane; r < GEMM_BM; r += 32) {
+                    if (m0 + r < g.M)
+                        l2_prefetch_bulk(g.epi.resid + static_cast<int64_t>(m0 + r) * g.epi.ldo + n0, cols * 4);
                 }
             }
         }
