@@ -32,6 +32,11 @@ def test_attention_three_shapes_single_tile_kernel():
     assert CE.stage_attention(force_v1=True)
 
 
+@pytest.mark.parametrize("variant", [5, 3])  # 5 = two-tile kernel with Q in tensor memory, 3 = experimental attention3
+def test_attention_three_shapes_other_variants(variant):
+    assert CE.stage_attention(variant=variant)
+
+
 def test_gemm_rejects_bad_arguments():
     from visrag_b200 import ops
 

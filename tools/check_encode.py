@@ -88,11 +88,11 @@ def _attn_ref(q, k, v, scale, causal):
     return torch.softmax(s, -1) @ v.float()
 
 
-def stage_attention(force_v1=False):
+def stage_attention(force_v1=False, variant=None):
     import torch
     from visrag_b200 import ops, _lib as L
 
-    L.lib().vr_attention_force_v1(1 if force_v1 else 0)
+    L.lib().vr_attention_force_v1(variant if variant is not None else (1 if force_v1 else 0))
     try:
         return _stage_attention_body(torch, ops)
     finally:
@@ -185,7 +185,7 @@ def stage_attention_perf():
     qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
     cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device="cuda")
     out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device="cuda")
-    for force in (0, 3, 1):
+    for force in (0, 5, 3, 1):
         L.lib().vr_attention_force_v1(force)
 
         def run():

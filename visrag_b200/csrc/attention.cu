@@ -55,11 +55,16 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
         } else {
             // sequences longer than one query tile: two 128-query tiles per CTA in ping-pong, P and O in tensor memory
             using Cfg2 = Att2Cfg<HS>;
-            auto kern = attention2_tcgen05_kernel<HS, CAUSAL>;
-            static bool attr_set = false;
-            if (!attr_set) {
+            // variant 5: Q in tensor memory as well (TS-MMA for Q.K^T). Measured SLOWER than Q in shared memory (1.20 vs
+            // 1.11 ms per ViT layer): the per-CTA prologue (row-wise global loads + tcgen05.st) and the extra TMEM reads
+            // cost more than the cheaper A operand saves. Needs 16-byte aligned Q rows.
+            const bool q_tmem = g_variant == 5 && p.ldq % 8 == 0 && p.q_col0 % 8 == 0 &&
+                                (reinterpret_cast<uintptr_t>(p.q) & 15) == 0;
+            auto kern = q_tmem ? attention2_tcgen05_kernel<HS, CAUSAL, true> : attention2_tcgen05_kernel<HS, CAUSAL, false>;
+            static bool attr_set[2] = {false, false};
+            if (!attr_set[q_tmem]) {
                 VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-                attr_set = true;
+                attr_set[q_tmem] = true;
             }
             dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
             kern<<<grid, ATT2_THREADS, Cfg2::SMEM_BYTES, stream>>>(maps, a);
@@ -80,7 +85,8 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
 
 }  // namespace vr
 
-// test hook: 0 = default kernels, 1 = force the single-tile kernel for every shape, 3 = experimental attention3 kernel
+// test hook: 0 = default kernels, 1 = force the single-tile kernel for every shape, 3 = experimental attention3 kernel,
+// 5 = two-tile kernel with Q in tensor memory too (slower; kept as a measured alternative)
 extern "C" void vr_attention_force_v1(int32_t variant) { vr::g_variant = variant; }
 
 extern "C" int vr_attention(const vr_attn_params* p, void* stream) {

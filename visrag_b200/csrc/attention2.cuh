@@ -13,7 +13,7 @@
 // whole S row fits in registers and is read from TMEM exactly once per key block.
 // Per-element ALU cost is cut with the sm_100 packed/3-input forms: FMNMX3 (max), FFMA2 (scale), FADD2 (sum), ex2.approx.
 //
-// TMEM (512 columns): S_A [0,128)  S_B [128,256)  PV_A [256,256+HS)  PV_B [384,384+HS).
+// TMEM (512 columns): S_A [0,128)  S_B [128,256)  PV_A [256,256+HS)  Q_A [256+HS, 256+1.5HS)  PV_B [384,384+HS)  Q_B behind it.
 #pragma once
 #include "attention.cuh"
 
@@ -60,7 +60,12 @@ __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, f
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
 }
 
-template <int HS, bool CAUSAL>
+// QT: the two Q tiles live in TENSOR MEMORY (written once by the softmax threads, global -> registers -> tcgen05.st,
+// packed bf16x2 in the HS/2 columns behind each tile's O accumulator) and S = Q K^T is a TS-MMA. With Q in shared
+// memory every Q.K MMA pays the ~128-cycle shared-memory A-operand read (640 cycles per tile and key block). MEASURED:
+// QT is slower in situ (1.20 vs 1.11 ms per ViT layer) - the prologue and the extra TMEM traffic outweigh the cheaper
+// operand - so the dispatcher uses QT = false; QT = true stays selectable (vr_attention_force_v1(5)) and tested.
+template <int HS, bool CAUSAL, bool QT>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a) {
     using Cfg = Att2Cfg<HS>;
@@ -76,7 +81,8 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
     uint64_t* s_bar = bars + 9;     // [2] per query tile
     uint64_t* p_bar = bars + 11;    // [2]
     uint64_t* o_bar = bars + 13;    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* q_ready = bars + 15;  // [2] QT only: the 128 rows of a Q tile are in TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qp = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -103,6 +109,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             mbar_init(&s_bar[i], 1);
             mbar_init(&p_bar[i], 128);
             mbar_init(&o_bar[i], 1);
+            mbar_init(&q_ready[i], 128);
         }
         fence_mbar_init();
     }
@@ -129,9 +136,11 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                 if (C1::HAS16) tma_load_2d(m16, bar, dst + C1::NCH * 16384, col + C1::NCH * 64, row);
             };
             const int qcol = a.q_col0 + head * HS, kcol = a.k_col0 + head * HS, vcol = a.v_col0 + head * HS;
-            mbar_expect_tx(q_bar, Cfg::TILE * (b_active ? 2 : 1));
-            load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QA, qcol, q_begin + q0);
-            if (b_active) load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QB, qcol, q_begin + q0 + ATT_BM);
+            if (!QT) {
+                mbar_expect_tx(q_bar, Cfg::TILE * (b_active ? 2 : 1));
+                load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QA, qcol, q_begin + q0);
+                if (b_active) load_tile(&maps.q64, &maps.q16, q_bar, smem + Cfg::OFF_QB, qcol, q_begin + q0 + ATT_BM);
+            }
             for (int j = 0; j < nkt; ++j) {
                 const int st = j & 1;
                 const uint32_t use_parity = (j >> 1) & 1;
@@ -155,16 +164,23 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
         const uint32_t kbase = smem_u32(smem + Cfg::OFF_K) >> 4, vbase = smem_u32(smem + Cfg::OFF_V) >> 4;
         constexpr uint32_t TILE16 = Cfg::TILE >> 4;
         // all addresses below are in 16-byte units (the descriptor's address field)
+        // q16: Q tile in shared memory (16-byte units) when !QT; with QT the A operand is the tile's TMEM copy
+        // (8 packed 32-bit columns per 16-element k-step) at d_tmem's tile: columns 256 + x*128 + HS
         auto issue_qk = [&](uint32_t q16, uint32_t k16, uint32_t d_tmem) {
+            const uint32_t qt = d_tmem + 256 + HS;  // d_tmem = tmem_base + x*128
             uint32_t acc = 0;
 #pragma unroll
             for (int c = 0; c < C1::NCH; ++c)
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    umma_f16_ss(d_tmem, hi128 | (q16 + c * 1024 + kk * 2), hi128 | (k16 + c * 1024 + kk * 2), idesc_qk, acc);
+                    if (QT) umma_f16_ts(d_tmem, qt + (c * 4 + kk) * 8, hi128 | (k16 + c * 1024 + kk * 2), idesc_qk, acc);
+                    else umma_f16_ss(d_tmem, hi128 | (q16 + c * 1024 + kk * 2), hi128 | (k16 + c * 1024 + kk * 2), idesc_qk, acc);
                     acc = 1;
                 }
-            if (C1::HAS16) umma_f16_ss(d_tmem, hi32 | (q16 + C1::NCH * 1024), hi32 | (k16 + C1::NCH * 1024), idesc_qk, acc);
+            if (C1::HAS16) {
+                if (QT) umma_f16_ts(d_tmem, qt + C1::NCH * 32, hi32 | (k16 + C1::NCH * 1024), idesc_qk, acc);
+                else umma_f16_ss(d_tmem, hi32 | (q16 + C1::NCH * 1024), hi32 | (k16 + C1::NCH * 1024), idesc_qk, acc);
+            }
         };
         // O (+)= P V : O lives in TMEM for the whole key loop; the first key block overwrites, later ones accumulate.
         // P is the A operand and is read from TENSOR MEMORY (it was written there by the softmax warps, packed bf16x2,
@@ -184,7 +200,12 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             }
         };
         const uint32_t tS0 = tmem_base, tS1 = tmem_base + 128, tO0 = tmem_base + 256, tO1 = tmem_base + 384;
-        mbar_wait(q_bar, 0);
+        if (QT) {
+            mbar_wait(&q_ready[0], 0);
+            if (b_active) mbar_wait(&q_ready[1], 0);
+        } else {
+            mbar_wait(q_bar, 0);
+        }
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
         if (elect_one()) {
@@ -254,6 +275,31 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
             // stale reference is kept (p <= 2^8 stays harmless in bf16/fp32, and O/l is invariant to the reference).
             constexpr float RESCALE_LOG2 = 8.0f;
             float m_ref = -INFINITY, l_run = 0.f;
+            if (QT) {  // this row of Q: global -> registers -> TMEM (packed bf16x2); rows past the sequence are zero
+                const uint32_t tmem_q = tmem_o + HS;
+                const uint4* src = reinterpret_cast<const uint4*>(a.q + static_cast<long long>(q_begin + q_idx) * a.ldq +
+                                                                  a.q_col0 + head * HS);
+                const bool valid = q_idx < len_q;
+                uint32_t w[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t = valid ? src[i] : make_uint4(0, 0, 0, 0);
+                    w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+                }
+                tmem_st_32x32(tmem_q, w);
+                if (HS == 80) {
+                    uint32_t w2[8];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint4 t = valid ? src[8 + i] : make_uint4(0, 0, 0, 0);
+                        w2[4 * i] = t.x; w2[4 * i + 1] = t.y; w2[4 * i + 2] = t.z; w2[4 * i + 3] = t.w;
+                    }
+                    tmem_st_32x8(tmem_q + 32, w2);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&q_ready[x]);
+            }
 
             for (int kt = 0; kt < nkt; ++kt) {
                 const uint32_t ph = kt & 1;
