@@ -65,6 +65,38 @@ __device__ __forceinline__ void pk_fma(float& d0, float& d1, float a0, float a1,
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(Cc));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
 }
+#ifndef VR_GELU_POLY
+#define VR_GELU_POLY 1
+#endif
+#if VR_GELU_POLY
+// erf without the SFU: z = clamp(x/sqrt2, +-3.2), erf(z) = z * P(u), u = z^2 * (2/3.2^2) - 1 in [-1, 1], P = degree-10
+// near-minimax polynomial (Chebyshev fit of erf(z)/z, evaluated by Horner in the mapped variable so the coefficients stay
+// O(1) and nothing cancels). |erf error| <= 3.2e-6 in fp32 incl. the clamp (1 - erf(3.2) = 6e-6), |GELU error| <= 1.2e-5
+// absolute - two orders below the bf16 rounding of the result. The Abramowitz-Stegun form below needs two MUFU ops per
+// element (rcp + ex2): 65536 per 128x256 tile = 4096 SFU cycles, the largest serial piece of the fc1 epilogue, which
+// was longer than the K = 1152 main loop. This form is 10.5 FMA-pipe instructions per element (packed FFMA2) and no MUFU.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    constexpr float R2 = 0.70710678118654752f, ZMAX = 3.2f, A = 2.0f / (ZMAX * ZMAX);
+    const float z0 = fminf(fmaxf(x0 * R2, -ZMAX), ZMAX), z1 = fminf(fmaxf(x1 * R2, -ZMAX), ZMAX);
+    float w0, w1, u0, u1, p0, p1;
+    pk_fma(w0, w1, z0, z1, z0, z1, 0.0f, 0.0f);
+    pk_fma(u0, u1, w0, w1, A, A, -1.0f, -1.0f);
+    pk_fma(p0, p1, u0, u1, 2.982273671e-03f, 2.982273671e-03f, -7.046153472e-03f, -7.046153472e-03f);
+    pk_fma(p0, p1, p0, p1, u0, u1, 7.957076705e-03f, 7.957076705e-03f);
+    pk_fma(p0, p1, p0, p1, u0, u1, -1.521942819e-02f, -1.521942819e-02f);
+    pk_fma(p0, p1, p0, p1, u0, u1, 3.318292224e-02f, 3.318292224e-02f);
+    pk_fma(p0, p1, p0, p1, u0, u1, -5.471928813e-02f, -5.471928813e-02f);
+    pk_fma(p0, p1, p0, p1, u0, u1, 8.062700147e-02f, 8.062700147e-02f);
+    pk_fma(p0, p1, p0, p1, u0, u1, -1.136467381e-01f, -1.136467381e-01f);
+    pk_fma(p0, p1, p0, p1, u0, u1, 1.543549678e-01f, 1.543549678e-01f);
+    pk_fma(p0, p1, p0, p1, u0, u1, -2.173077339e-01f, -2.173077339e-01f);
+    pk_fma(p0, p1, p0, p1, u0, u1, 4.413341836e-01f, 4.413341836e-01f);
+    float r0, r1;
+    pk_fma(r0, r1, p0, p1, z0, z1, 0.0f, 0.0f);  // erf(z)
+    const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+    pk_fma(x0, x1, h0, h1, r0, r1, h0, h1);
+}
+#else
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
     constexpr float R2 = 0.70710678118654752f;
     const float a0 = fabsf(x0) * R2, a1 = fabsf(x1) * R2;  // |z|, z = x / sqrt(2)
@@ -86,7 +118,14 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
     const float h0 = 0.5f * x0, h1 = 0.5f * x1;
     pk_fma(x0, x1, h0, h1, r0, r1, h0, h1);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+#endif
+// x * sigmoid(x) with two SFU ops (ex2 + rcp, ~1e-6 relative) instead of an IEEE division
+__device__ __forceinline__ float silu(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 
 // ---------------------------------------------------------------------------------------
 // Epilogue. tcgen05.ld hands every thread ONE output row (32 consecutive columns per chunk), which is the wrong shape
