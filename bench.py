@@ -97,6 +97,9 @@ def total_flops_per_page(n_patches: int, lm_tokens: int) -> float:
 
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(a):
+    # NCCL prints "NCCL version ..." on STDOUT at the VERSION level; stdout must carry exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy as np
     import torch
     import torch.distributed as dist
