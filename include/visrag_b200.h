@@ -100,8 +100,9 @@ int vr_resample_u8(const uint8_t* src, int32_t n, int32_t in_h, int32_t in_w, co
                    uint8_t* out, const int32_t* first_cell, int32_t cell_h, int32_t cell_w, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * Fused softmax(Q K^T * scale) V on tcgen05 (S and the P.V partial product live in TMEM,
- * P is re-staged through 128B-swizzled shared memory, running max/sum/O in registers).
+ * Fused softmax(Q K^T * scale) V on tcgen05. Sequences longer than 128 queries: two query tiles per CTA, S, P
+ * (bf16, TS-MMA operand) and the O accumulator all live in TMEM, lazy rescaling. Up to 128 queries per sequence:
+ * single-tile kernel, P re-staged through 128B-swizzled shared memory, running max/sum/O in registers.
  * Replaces F.scaled_dot_product_attention in timm/models/vision_transformer.py:92-96 (ViT,
  * 16 heads x 72, no mask), modeling_minicpm.py:895-903 (MiniCPM, causal + right padding ->
  * here: packed var-len sequences, no padding rows at all) and nn.MultiheadAttention in

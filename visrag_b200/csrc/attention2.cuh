@@ -345,7 +345,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                     }
                     m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 }
-                // previous P.V must have retired before P smem is overwritten (and before O is rescaled)
+                // previous P.V must have retired before P (TMEM, over this tile's S columns) is overwritten and before O is rescaled
                 if (kt > 0) {
                     mbar_wait(&o_bar[x], ph ^ 1);
                     tc_fence_after();
@@ -380,7 +380,7 @@ attention2_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a)
                     tmem_st_wait();
                 }
                 const float neg_ms = -m_ref * sl2;
-                // p = 2^(s*scale*log2e - m_ref*scale*log2e), bf16 into the 128B-swizzled P tile
+                // p = 2^(s*scale*log2e - m_ref*scale*log2e), packed bf16x2 into tensor memory (the A operand of the P.V TS-MMA)
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {

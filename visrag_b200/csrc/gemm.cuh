@@ -36,6 +36,7 @@ struct GemmCfg {
 
 struct GemmArgs {
     int M, N, K;
+    int prefetch_resid;  // 1: warp 3 pulls the fp32 residual tile into L2 ahead of the epilogue (set by the launcher)
     vr_gemm_epilogue epi;
 };
 
@@ -511,8 +512,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // pulls tile i's residual rows into L2 while tile i's main loop runs, one tile ahead of the epilogue. Pacing is
         // a monotonic counter published by the MMA warp (not an mbarrier phase: a phase can be missed by a late
         // waiter, a counter cannot), and a tile whose main loop is already over is skipped.
-        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.epi.resid != nullptr && (g.epi.ldo & 3) == 0 &&
-            (reinterpret_cast<uintptr_t>(g.epi.resid) & 15) == 0) {
+        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.prefetch_resid) {
             int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
                 uint32_t started;

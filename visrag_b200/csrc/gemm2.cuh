@@ -136,8 +136,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     } else if (warp == 3) {
         // ------------------------------------------------------------ residual prefetcher (both CTAs, own 128 rows);
         // see gemm.cuh: pulls tile i's fp32 residual rows into L2 while tile i's main loop runs
-        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.epi.resid != nullptr && (g.epi.ldo & 3) == 0 &&
-            (reinterpret_cast<uintptr_t>(g.epi.resid) & 15) == 0) {
+        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.prefetch_resid) {
             int it = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 uint32_t started;

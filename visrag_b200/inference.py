@@ -44,47 +44,77 @@ def _dump(output_dir: str, name: str, encoded: List[np.ndarray], lookup: List[st
         pickle.dump((np.concatenate(encoded) if encoded else np.zeros((0, 0), np.float32), lookup), f, protocol=4)
 
 
+def _split_batch(batch: dict, parts: int) -> List[dict]:
+    n = len(batch["id"])
+    parts = max(1, min(parts, n))
+    bounds = [n * i // parts for i in range(parts + 1)]
+    return [{k: v[a:b] for k, v in batch.items()} for a, b in zip(bounds, bounds[1:]) if b > a]
+
+
 @torch.no_grad()
-def encode_stream(batches: Iterable[dict], model, model_additional_args: Optional[dict] = None):
+def encode_stream(batches: Iterable[dict], model, model_additional_args: Optional[dict] = None, ramp_parts: int = 4):
     """Pipelined encode: yields (ids, float32 ndarray [n, d]) per batch, in order.
 
     Three things overlap: the host preparation of batch i+1 (PIL resampling, tokenisation; worker thread), the kernels
     of batch i (asynchronous launches on the current stream) and the device->host copy of batch i-1 (pinned buffer +
-    event instead of the reference's blocking `.cpu()`, `inference.py:98`)."""
+    event instead of the reference's blocking `.cpu()`, `inference.py:98`). The FIRST batch is cut into `ramp_parts`
+    pieces so that the GPU starts after a fraction of a batch has been prepared instead of idling through the whole
+    first preparation (the pipeline fill); its pieces are re-joined before it is yielded."""
     from collections import deque
     from concurrent.futures import ThreadPoolExecutor
 
     kw = model_additional_args or {}
-    it = iter(batches)
-    first = next(it, None)
-    if first is None:
+
+    def work_items():  # (batch, is_last_piece_of_its_batch)
+        first = True
+        for b in batches:
+            pieces = _split_batch(b, ramp_parts) if first and len(b["id"]) >= 4 * ramp_parts else [b]
+            first = False
+            for i, piece in enumerate(pieces):
+                yield piece, i == len(pieces) - 1
+
+    it = work_items()
+    cur = next(it, None)
+    if cur is None:
         return
     pending = deque()
+    joined_ids: List[str] = []
+    joined: List[np.ndarray] = []
 
     def collect():
-        ids, host, ev = pending.popleft()
+        ids, host, ev, last = pending.popleft()
         ev.synchronize()
-        return ids, host.numpy().copy()
+        joined_ids.extend(ids)
+        joined.append(host.numpy().copy())
+        if not last:
+            return None
+        out = (list(joined_ids), joined[0] if len(joined) == 1 else np.concatenate(joined))
+        joined_ids.clear()
+        joined.clear()
+        return out
 
     with ThreadPoolExecutor(max_workers=1) as pool:
-        fut = pool.submit(model.prepare, first, **kw)
-        cur = first
+        fut = pool.submit(model.prepare, cur[0], **kw)
         while cur is not None:
             pb = fut.result()
             nxt = next(it, None)
             if nxt is not None:
-                fut = pool.submit(model.prepare, nxt, **kw)
+                fut = pool.submit(model.prepare, nxt[0], **kw)
             reps = model.encode_prepared(pb)
             host = torch.empty(reps.shape, dtype=torch.float32).pin_memory()
             host.copy_(reps, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-            pending.append((cur["id"], host, ev))
+            pending.append((cur[0]["id"], host, ev, cur[1]))
             if len(pending) > 1:
-                yield collect()
+                out = collect()
+                if out is not None:
+                    yield out
             cur = nxt
     while pending:
-        yield collect()
+        out = collect()
+        if out is not None:
+            yield out
 
 
 @torch.no_grad()
