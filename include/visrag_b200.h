@@ -86,10 +86,12 @@ int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t ldb, int32_
  * [row_first, row_first+row_count) into an 8-bit intermediate, then the vertical pass, 22-bit fixed-point
  * coefficients, 32-bit sums, clip8. Results are bit-identical to PIL.
  *   src        [n, in_h, in_w, 3] uint8 (n pages of one size)
- *   bounds_*   [out, 2] int32 (first source index, tap count), coeffs_* [out, ksize_*] int32 fixed point, as
- *              Pillow's precompute_coeffs + normalize_coeffs_8bpc produce them (frontend.resample_coeffs);
- *              NULL for an axis whose size does not change (Pillow skips that pass)
- *   tmp        workspace [n, row_count, out_w, 3] uint8, needed when both passes run
+ *   bounds_*   [out, 2] int32 (first source index, tap count); coefficients int32 fixed point as Pillow's
+ *              precompute_coeffs + normalize_coeffs_8bpc produce them (frontend.resample_coeffs): coeffs_v
+ *              [out_h, ksize_v] (row per output row), coeffs_h TAP-MAJOR [ksize_h, out_w] (coalesced across the
+ *              threads of the horizontal pass); NULL for an axis whose size does not change (Pillow skips that
+ *              pass). in_w <= 16384.
+ *   tmp        workspace of n * row_count * ((out_w*3 + 3) & ~3) bytes (4-byte row pitch), needed when both passes run
  *   out        slice buffer [*, cell_h, cell_w, 3] uint8: the out_h x out_w result of page i is cut into
  *              (out_h/cell_h) x (out_w/cell_w) cells, row-major, stored as slices first_cell[i], first_cell[i]+1, ...
  *              (cell = whole image for the thumbnail). first_cell: [n] int32, device.

@@ -76,17 +76,20 @@ class DeviceFrontEnd:
         self.device = device
         self._tables = {}
 
-    def _axis(self, n_in: int, n_out: int):
-        """-> (ksize, bounds_dev, coeffs_dev, first_row, row_count) or None when the axis keeps its size."""
+    def _axis(self, n_in: int, n_out: int, tap_major: bool):
+        """-> (ksize, bounds_dev, coeffs_dev, first_row, row_count) or None when the axis keeps its size.
+        `tap_major`: coefficients as [ksize, out] (the horizontal pass reads them coalesced) instead of [out, ksize]."""
         import torch
 
         if n_in == n_out:
             return None
-        key = (n_in, n_out)
+        key = (n_in, n_out, tap_major)
         if key not in self._tables:
             ksize, bounds, kk = resample_coeffs(n_in, n_out)
             first = int(bounds[0, 0])
             last = int(bounds[-1, 0] + bounds[-1, 1])
+            if tap_major:
+                kk = np.ascontiguousarray(kk.T)
             self._tables[key] = (ksize, torch.from_numpy(bounds).to(self.device), torch.from_numpy(kk).to(self.device),
                                  first, last - first)
         return self._tables[key]
@@ -97,14 +100,14 @@ class DeviceFrontEnd:
         from . import _lib as L
 
         n, H, W, _ = pages.shape
-        h = self._axis(W, out_w)
-        v = self._axis(H, out_h)
+        h = self._axis(W, out_w, True)
+        v = self._axis(H, out_h, False)
         tmp = None
         r0, rc = (v[3], v[4]) if v is not None else (0, H)
         if h is not None and v is not None:
             import torch
 
-            tmp = torch.empty((n, rc, out_w, 3), dtype=torch.uint8, device=pages.device)
+            tmp = torch.empty((n, rc, (out_w * 3 + 3) & ~3), dtype=torch.uint8, device=pages.device)  # 4-byte row pitch
         L.check(L.lib().vr_resample_u8(
             pages.data_ptr(), n, H, W,
             h[1].data_ptr() if h else None, h[2].data_ptr() if h else None, h[0] if h else 0,

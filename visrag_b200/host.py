@@ -143,7 +143,7 @@ def _tokenize(content: str, tokenizer, max_inp_length: Optional[int]) -> Tuple[n
     return ids, bound
 
 
-MAX_DEVICE_PAGE_WIDTH = 160 * 1024 // 3  # vr_resample_u8 stages one source row in shared memory
+MAX_DEVICE_PAGE_WIDTH = 16384  # vr_resample_u8 stages four source rows in shared memory
 
 
 @dataclass
