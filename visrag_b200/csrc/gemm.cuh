@@ -208,21 +208,34 @@ __device__ __forceinline__ void stage_store_half(const uint8_t* st, int lane, __
 }
 
 // LINEAR: out = [resid +] scale * gelu?(acc + bias) [+ rowadd[row % period]]   (one 32-column chunk of one warp)
+// The bias of the warp's COLS_PER_WARP (<= 128) columns is fetched ONCE per tile, before the wait for the accumulator
+// (epi_bias_prefetch: lane l holds columns 4l..4l+3 of the warp's span, zeros past N), and handed to the chunks by warp
+// shuffles. Loading it per chunk (8 x LDG.128 per thread) put an L1/L2 round trip on the critical path of every chunk:
+// 17 % of the fc1 kernel's stall samples sat on the bias FADDs.
+__device__ __forceinline__ float4 epi_bias_prefetch(const GemmArgs& g, int lane, int col_first, int cols_per_warp) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = col_first + lane * 4;
+    if (g.epi.bias && lane * 4 < cols_per_warp && c < g.N) b = *reinterpret_cast<const float4*>(g.epi.bias + c);  // N % 8 == 0
+    return b;
+}
+
 template <bool OUT_F32, bool GELU>
-__device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&x)[32]) {
+__device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&x)[32],
+                                           const float4& bias4, int chunk) {
     const vr_gemm_epilogue& e = g.epi;
     const int rows_valid = g.M - row0;          // may exceed 32
     const int cols_valid = g.N - col0;          // may exceed 32; N % 8 == 0
-    if (rows_valid <= 0 || cols_valid <= 0) return;  // warp-uniform
-    if (e.bias) {
+    if (e.bias) {  // shuffles are warp collective: before the (warp-uniform) early exit anyway
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-            if (j4 * 4 < cols_valid) {
-                const float4 b = *reinterpret_cast<const float4*>(e.bias + col0 + j4 * 4);
-                x[j4 * 4] += b.x; x[j4 * 4 + 1] += b.y; x[j4 * 4 + 2] += b.z; x[j4 * 4 + 3] += b.w;
-            }
+            const int src = chunk * 8 + j4;
+            x[j4 * 4] += __shfl_sync(0xffffffffu, bias4.x, src);
+            x[j4 * 4 + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
+            x[j4 * 4 + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
+            x[j4 * 4 + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
         }
     }
+    if (rows_valid <= 0 || cols_valid <= 0) return;  // warp-uniform
     if (GELU) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) gelu_erf2(x[j], x[j + 1]);
@@ -544,6 +557,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n0 = tile_n0(t);
             const int row0 = m0 + quarter * 32;  // first of this warp's 32 rows
             uint8_t* st = smem_stage + ew * Cfg::EPI_STAGE_BYTES;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == VR_EPI_LINEAR && !SWAP) bias4 = epi_bias_prefetch(g, lane, n0 + half * COLS_PER_WARP, COLS_PER_WARP);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
@@ -563,7 +578,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     if (SWAP) epi_linear_t<OUT_F32, GELU>(g, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
-                    else epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
+                    else epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v, bias4, c);
                 }
             } else {
 #pragma unroll 1
