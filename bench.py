@@ -95,6 +95,12 @@ def total_flops_per_page(n_patches: int, lm_tokens: int) -> float:
             + 4_883_742_720.0 * lm_tokens + 184_320.0 * lm_tokens ** 2)
 
 
+def workload_name(a) -> str:
+    """Both arms measure the same thing: pages/s of this workload (BASELINE.json configs[2])."""
+    return (f"BASELINE configs[2]: full VisRAG-Ret (SigLIP-so400m x26 + Resampler + MiniCPM-2B x40) encode of synthetic "
+            f"{a.page_px}x{a.page_px} pages")
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(a):
     # NCCL prints "NCCL version ..." on STDOUT at the VERSION level; stdout must carry exactly one JSON line
@@ -292,8 +298,7 @@ def run_ours(a):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: full VisRAG-Ret (SigLIP-so400m x26 + Resampler + MiniCPM-2B x40) encode of "
-                                   f"synthetic {a.page_px}x{a.page_px} pages; {nq} text queries top-10 over {nd * world} pages",
+            "config": {"workload": workload_name(a), "queries": f"{nq} text queries top-10 over {nd * world} pages",
                        "model": a.model, "pages_per_step_per_gpu": P, "global_batch": P * world, "patches_per_page": n_patches,
                        "lm_tokens_per_page": lm_tokens, "parallelism": f"dp{world} (pages sharded, no encode collective)",
                        "weights": "random-init, bf16", "l2": "working set (6.3 GB weights + >1 GB activations per step) >> 126 MB L2"},
@@ -402,7 +407,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[2]: full VisRAG-Ret encode of synthetic {a.page_px}x{a.page_px} pages", "model": a.model},
+        "config": {"workload": workload_name(a), "model": a.model, "pages_per_step_per_gpu": 1,
+                   "sample": "each step is ONE page of the workload through the full model on the host cores"},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

@@ -60,3 +60,25 @@ def test_knowledge_base_files_match_the_demo_layout(tmp_path):
     with pytest.raises(ValueError):
         KB.save_knowledge_base(str(tmp_path / "kb2"), reps, names[:4])
     assert KB.DEMO_QUERY_PREFIX.endswith("document: ")
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the host-cores arm) must print ONE JSON line with the contract's keys; run here on
+    the tiny model so that it takes seconds."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "tiny", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "page-images encoded/sec" and d["unit"] == "pages/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] >= 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "configs[2]" in d["config"]["workload"]
