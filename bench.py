@@ -103,9 +103,6 @@ def workload_name(a) -> str:
 
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(a):
-    # NCCL prints "NCCL version ..." on STDOUT at the VERSION level; stdout must carry exactly one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -125,7 +122,19 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # NCCL writes its "NCCL version ..." banner to STDOUT when the first communicator is created (whenever NCCL_DEBUG
+        # is set, as it is on the GPU boxes); stdout must carry exactly one JSON line, so the banner is sent to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = VisRAGConfig.full() if a.model == "full" else VisRAGConfig.tiny()
     tok = StubTokenizer(cfg.vocab)
     t0 = time.time()
