@@ -176,6 +176,20 @@ class PreparedBatch:
                 + sum(j.pixels.nbytes for j in self.jobs))
 
 
+_POOL_WORKERS = 8
+_pool_obj = None
+
+
+def _pool():
+    """Process-wide worker pool for per-page host work (created on first use; threads are daemonic helpers)."""
+    global _pool_obj
+    if _pool_obj is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _pool_obj = ThreadPoolExecutor(max_workers=_POOL_WORKERS, thread_name_prefix="visrag-host")
+    return _pool_obj
+
+
 def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAGConfig,
                   max_inp_length: Optional[int] = 2048, device_frontend: bool = False) -> PreparedBatch:
     """Everything `VisRAG_Ret.forward` does before `get_vllm_embedding` (`modeling_visrag_ret.py:96-111`).
@@ -203,13 +217,18 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
         return [], text
 
     n_img = sum(1 for im in images if im)
-    if n_img >= 8:  # PIL resampling / packing release the GIL; the reference uses ThreadPoolExecutor(8) here too
-        from concurrent.futures import ThreadPoolExecutor
-
-        with ThreadPoolExecutor(max_workers=8) as ex:
-            prepared = list(ex.map(one, zip(texts, images)))
+    items = list(zip(texts, images))
+    # Threads only pay off when PIL resamples on the host (Image.resize releases the GIL; the reference uses
+    # ThreadPoolExecutor(8) for the same reason). What is left with the device front-end - PIL's tobytes() behind
+    # np.asarray - holds the GIL: measured 55 ms per 128 pages on one thread, 72 ms on eight.
+    if n_img >= 8 and not device_frontend:
+        # one persistent pool and one task per worker: creating a pool and 128 futures per batch cost more than the work
+        n_chunks = min(_POOL_WORKERS, len(items))
+        bounds = [len(items) * i // n_chunks for i in range(n_chunks + 1)]
+        parts = _pool().map(lambda ab: [one(it) for it in items[ab[0]:ab[1]]], zip(bounds, bounds[1:]))
+        prepared = [r for part in parts for r in part]
     else:
-        prepared = [one(it) for it in zip(texts, images)]
+        prepared = [one(it) for it in items]
     for (slices, content), image in zip(prepared, images):
         ids, bound = tokenize(content, tokenizer, max_inp_length)
         if isinstance(slices, PageJob) and len(bound) != slices.plan.n_slices:
