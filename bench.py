@@ -221,7 +221,8 @@ def run_ours(a):
     barrier()
     blocking_ms = max_over_ranks(e0.elapsed_time(e1))
     blocking_value = world * a.steps * P / (blocking_ms / 1e3)
-    h2d = int(pb.pixel_bytes() + pb.token_src.nbytes + pb.positions.nbytes + pb.cu_seqlens.nbytes)
+    pb_e2e = model.prepare(stream_items, **kw)  # what the e2e path really uploads (raw RGBX pages with the device front-end)
+    h2d = int(pb_e2e.pixel_bytes() + pb_e2e.token_src.nbytes + pb_e2e.positions.nbytes + pb_e2e.cu_seqlens.nbytes)
     d2h = int(host_reps.numel() * 4)
     assert torch.isfinite(host_reps).all()
 

@@ -85,18 +85,20 @@ int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t ldb, int32_
  * Pillow's ImagingResample (src/libImaging/Resample.c): horizontal pass over source rows
  * [row_first, row_first+row_count) into an 8-bit intermediate, then the vertical pass, 22-bit fixed-point
  * coefficients, 32-bit sums, clip8. Results are bit-identical to PIL.
- *   src        [n, in_h, in_w, 3] uint8 (n pages of one size)
+ *   src        [n, in_h, in_w, src_pixel_bytes] uint8 (n pages of one size); src_pixel_bytes = 3 (packed RGB) or
+ *              4 (RGBX: Pillow's native row layout for mode "RGB", so a page can travel without any repacking on
+ *              the host; the 4th byte is ignored)
  *   bounds_*   [out, 2] int32 (first source index, tap count); coefficients int32 fixed point as Pillow's
  *              precompute_coeffs + normalize_coeffs_8bpc produce them (frontend.resample_coeffs): coeffs_v
  *              [out_h, ksize_v] (row per output row), coeffs_h TAP-MAJOR [ksize_h, out_w] (coalesced across the
  *              threads of the horizontal pass); NULL for an axis whose size does not change (Pillow skips that
- *              pass). in_w <= 16384.
+ *              pass). in_w <= 12288.
  *   tmp        workspace of n * row_count * ((out_w*3 + 3) & ~3) bytes (4-byte row pitch), needed when both passes run
  *   out        slice buffer [*, cell_h, cell_w, 3] uint8: the out_h x out_w result of page i is cut into
  *              (out_h/cell_h) x (out_w/cell_w) cells, row-major, stored as slices first_cell[i], first_cell[i]+1, ...
  *              (cell = whole image for the thumbnail). first_cell: [n] int32, device.
  * ---------------------------------------------------------------------------------- */
-int vr_resample_u8(const uint8_t* src, int32_t n, int32_t in_h, int32_t in_w, const int32_t* bounds_h,
+int vr_resample_u8(const uint8_t* src, int32_t src_pixel_bytes, int32_t n, int32_t in_h, int32_t in_w, const int32_t* bounds_h,
                    const int32_t* coeffs_h, int32_t ksize_h, const int32_t* bounds_v, const int32_t* coeffs_v,
                    int32_t ksize_v, int32_t row_first, int32_t row_count, int32_t out_h, int32_t out_w, uint8_t* tmp,
                    uint8_t* out, const int32_t* first_cell, int32_t cell_h, int32_t cell_w, void* stream);

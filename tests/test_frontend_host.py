@@ -60,17 +60,19 @@ def test_device_jobs_reproduce_the_host_layout():
         assert np.array_equal(getattr(host, f), getattr(dev, f)), f
     assert host.group_row0 == dev.group_row0 and host.n_slices == dev.n_slices
     assert {k: len(v) for k, v in host.groups.items()} == {k: len(v) for k, v in dev.groups.items()}
-    # the 448x448 page needs no resampling and stays on the host path; every other slice is a device job's
-    assert len(dev.jobs) == len(pages) - 1
-    assert sum(a is not None for lst in dev.groups.values() for a in lst) == 1
+    # every page is a device job (the 448x448 one is a plain copy there); pixels travel as Pillow's RGBX rows
+    assert len(dev.jobs) == len(pages) and all(a is None for lst in dev.groups.values() for a in lst)
+    assert all(j.pixels.dtype == np.uint8 and j.pixels.shape[2] in (3, 4) for j in dev.jobs)
+    assert all(np.array_equal(j.pixels[..., :3], np.asarray(p)) for j, p in zip(dev.jobs, pages))
     # execute the jobs with the oracle resampler and compare slice by slice with the PIL-rendered groups
     filled = {k: [None] * len(v) for k, v in dev.groups.items()}
     for j in dev.jobs:
         p = j.plan
         key, idx = j.thumb
-        filled[key][idx] = PR.resize_bicubic(j.pixels, *p.source_size)
+        rgb = np.ascontiguousarray(j.pixels[..., :3])
+        filled[key][idx] = PR.resize_bicubic(rgb, *p.source_size)
         if p.grid is not None:
-            ref = PR.resize_bicubic(j.pixels, *p.refine_size)
+            ref = PR.resize_bicubic(rgb, *p.refine_size)
             cw, ch = p.cell_size
             key, idx = j.cells
             for cy in range(p.grid[1]):
@@ -104,3 +106,13 @@ def test_truncated_page_falls_back_to_host_rendering():
     for k, lst in host_cut.groups.items():
         for a, b in zip(lst, cut.groups[k]):
             assert b is None or np.array_equal(a, b)
+
+
+def test_page_pixels_exports_pillow_rows_without_repacking():
+    """RGBX zero-copy export when Pillow + pyarrow provide it, RGB otherwise; other modes are converted first."""
+    rs = np.random.RandomState(1)
+    arr = rs.randint(0, 256, (37, 53, 3), dtype=np.uint8)
+    for im in (Image.fromarray(arr), Image.fromarray(arr).crop((3, 2, 40, 30)), Image.fromarray(arr[..., 0]), Image.fromarray(arr).convert("RGBA")):
+        px = F.page_pixels(im)
+        assert px.dtype == np.uint8 and px.shape[:2] == (im.size[1], im.size[0]) and px.shape[2] in (3, 4)
+        assert np.array_equal(px[..., :3], np.asarray(im.convert("RGB")))

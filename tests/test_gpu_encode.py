@@ -137,9 +137,9 @@ def test_encode_stream_equals_blocking_calls():
         want = model(passage=batch, **kw).p_reps.cpu().numpy()
         assert np.array_equal(got[b], want)
     assert list(I.encode_stream([], model, kw)) == []
-    # a first batch large enough to be ramped (cut into 4 pieces, re-joined before it is yielded)
+    # a ramped first batch (cut into 4 pieces, re-joined before it is yielded)
     big = [{"id": f"r{i}", "text": "", "image": pages[i % len(pages)]} for i in range(19)]
-    out = list(I.encode_stream(I._batches(big, 17), model, kw))
+    out = list(I.encode_stream(I._batches(big, 17), model, kw, ramp_parts=4))
     assert [len(ids) for ids, _ in out] == [17, 2] and out[0][0] == [d["id"] for d in big[:17]]
     want = model(passage=I.naive_collator(big[:17]), **kw).p_reps.cpu().numpy()
     assert np.array_equal(out[0][1], want)

@@ -21,8 +21,9 @@ def _pil(img, ow, oh):
     return np.asarray(Image.fromarray(img).resize((ow, oh), Image.Resampling.BICUBIC))
 
 
+@pytest.mark.parametrize("rgbx", [False, True])
 @pytest.mark.parametrize("W,H,ow,oh,cw,ch", CASES)
-def test_resampler_equals_pillow(W, H, ow, oh, cw, ch):
+def test_resampler_equals_pillow(W, H, ow, oh, cw, ch, rgbx):
     from visrag_b200.frontend import DeviceFrontEnd
 
     fe = DeviceFrontEnd(torch.device("cuda:0"))
@@ -36,7 +37,10 @@ def test_resampler_equals_pillow(W, H, ow, oh, cw, ch):
     # pages land in a shuffled order with a gap slice in between, like slices of different pages sharing a group
     first = np.asarray([cells + 1, 0, 2 * cells + 2], dtype=np.int32)
     out = torch.full((3 * cells + 3, ch, cw, 3), 7, dtype=torch.uint8, device="cuda:0")
-    fe.resize_into(torch.from_numpy(pages).cuda(), ow, oh, out, torch.from_numpy(first).cuda(), cw, ch)
+    src = pages
+    if rgbx:  # Pillow's native row layout: 4 bytes per pixel, the 4th is padding (garbage here on purpose)
+        src = np.concatenate([pages, rs.randint(0, 256, (n, H, W, 1), dtype=np.uint8)], axis=3)
+    fe.resize_into(torch.from_numpy(src).cuda(), ow, oh, out, torch.from_numpy(first).cuda(), cw, ch)
     got = out.cpu().numpy()
     for i in range(n):
         want = _pil(pages[i], ow, oh)
@@ -54,11 +58,14 @@ def test_bad_arguments_are_rejected():
     f = torch.zeros(1, dtype=torch.int32, device="cuda:0")
     lib = L.lib()
     # width changes but no horizontal tables
-    rc = lib.vr_resample_u8(z.data_ptr(), 1, 2, 2, None, None, 0, None, None, 0, 0, 2, 2, 4, None, z.data_ptr(), f.data_ptr(), 2, 4, None)
+    rc = lib.vr_resample_u8(z.data_ptr(), 3, 1, 2, 2, None, None, 0, None, None, 0, 0, 2, 2, 4, None, z.data_ptr(), f.data_ptr(), 2, 4, None)
     assert rc != 0 and b"horizontal" in lib.vr_last_error()
     # output not a whole grid of cells
-    rc = lib.vr_resample_u8(z.data_ptr(), 1, 2, 2, None, None, 0, None, None, 0, 0, 2, 2, 2, None, z.data_ptr(), f.data_ptr(), 2, 3, None)
+    rc = lib.vr_resample_u8(z.data_ptr(), 3, 1, 2, 2, None, None, 0, None, None, 0, 0, 2, 2, 2, None, z.data_ptr(), f.data_ptr(), 2, 3, None)
     assert rc != 0 and b"grid" in lib.vr_last_error()
+    # only RGB / RGBX sources
+    rc = lib.vr_resample_u8(z.data_ptr(), 2, 1, 2, 2, None, None, 0, None, None, 0, 0, 2, 2, 2, None, z.data_ptr(), f.data_ptr(), 2, 2, None)
+    assert rc != 0 and b"src_pixel_bytes" in lib.vr_last_error()
 
 
 def test_encode_with_device_frontend_is_bit_identical():

@@ -92,7 +92,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.vr_score_exact.restype = i32
     lib.vr_score_exact.argtypes = [vp, i32, vp, i64, i32, vp, vp]
     lib.vr_resample_u8.restype = i32
-    lib.vr_resample_u8.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp]
+    lib.vr_resample_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp]
     lib.vr_topk_rows_chunked.restype = i32
     lib.vr_topk_rows_chunked.argtypes = [vp, i32, i64, i32, i64, i32, vp, vp, vp, vp, vp]
     lib.vr_topk_rows.restype = i32

@@ -54,11 +54,11 @@ __device__ __forceinline__ void rs_stage_row(uint8_t* dst, const uint8_t* __rest
 }
 
 __global__ void __launch_bounds__(256)
-resample_h_kernel(const uint8_t* __restrict__ src, int in_h, int in_w, int row0, int rows, const int32_t* __restrict__ bounds,
-                  const int32_t* __restrict__ kk, int out_w, RsDst dst) {
+resample_h_kernel(const uint8_t* __restrict__ src, int in_h, int in_w, int ps, int row0, int rows,
+                  const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int out_w, RsDst dst) {
     extern __shared__ uint8_t rowbuf[];
     const int y0 = blockIdx.x * RS_ROWS, img = blockIdx.y;
-    const int nbytes = in_w * 3;
+    const int nbytes = in_w * ps;  // ps = source bytes per pixel: 3 (packed RGB) or 4 (Pillow's native RGBX rows)
     const int pitch = (nbytes + 3) & ~3;
     const int nrows = min(RS_ROWS, rows - y0);
     for (int r = 0; r < nrows; ++r)
@@ -69,12 +69,12 @@ resample_h_kernel(const uint8_t* __restrict__ src, int in_h, int in_w, int row0,
         int acc[RS_ROWS][3];
 #pragma unroll
         for (int r = 0; r < RS_ROWS; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (RS_PRECISION_BITS - 1);
-        const uint8_t* p = rowbuf + xmin * 3;
+        const uint8_t* p = rowbuf + xmin * ps;
         for (int j = 0; j < n; ++j) {
             const int c = kk[static_cast<int64_t>(j) * out_w + xx];
 #pragma unroll
             for (int r = 0; r < RS_ROWS; ++r) {
-                const uint8_t* q = p + r * pitch + 3 * j;  // rows past nrows read stale shared memory; never stored
+                const uint8_t* q = p + r * pitch + ps * j;  // rows past nrows read stale shared memory; never stored
                 acc[r][0] += q[0] * c;
                 acc[r][1] += q[1] * c;
                 acc[r][2] += q[2] * c;
@@ -94,7 +94,7 @@ resample_h_kernel(const uint8_t* __restrict__ src, int in_h, int in_w, int row0,
 // source rows. WORDS: the source is the 4-byte-pitched intermediate of the horizontal pass -> 32-bit loads, 4 bytes per thread.
 template <bool WORDS>
 __global__ void __launch_bounds__(256)
-resample_v_kernel(const uint8_t* __restrict__ src, int in_rows, int w, int pitch, const int32_t* __restrict__ bounds,
+resample_v_kernel(const uint8_t* __restrict__ src, int in_rows, int w, int pitch, int ps, const int32_t* __restrict__ bounds,
                   const int32_t* __restrict__ kk, int ksize, int shift, RsDst dst) {
     const int yy = blockIdx.x, img = blockIdx.y;
     const int ymin = bounds[2 * yy] - shift, n = bounds[2 * yy + 1];
@@ -124,28 +124,39 @@ resample_v_kernel(const uint8_t* __restrict__ src, int in_rows, int w, int pitch
         }
     } else {
         for (int b = threadIdx.x; b < nbytes; b += blockDim.x) {
+            const int x = b / 3, ch = b - x * 3;
+            const int off = x * ps + ch;  // byte of (pixel x, channel ch) inside a source row
             int s = 1 << (RS_PRECISION_BITS - 1);
-            for (int j = 0; j < n; ++j) s += col[static_cast<int64_t>(j) * pitch + b] * k[j];
-            const int x = b / 3;
-            rs_dst(dst, img, yy, x)[b - x * 3] = rs_clip8(s);
+            for (int j = 0; j < n; ++j) s += col[static_cast<int64_t>(j) * pitch + off] * k[j];
+            rs_dst(dst, img, yy, x)[ch] = rs_clip8(s);
         }
     }
 }
 
 // ---- no resampling at all (Image.resize to the same size is a copy): scatter rows into the cell layout
 __global__ void __launch_bounds__(256)
-resample_copy_kernel(const uint8_t* __restrict__ src, int h, int w, RsDst dst) {
+resample_copy_kernel(const uint8_t* __restrict__ src, int h, int w, int ps, RsDst dst) {
     const int y = blockIdx.x, img = blockIdx.y;
-    const uint8_t* line = src + (static_cast<int64_t>(img) * h + y) * w * 3;
-    for (int b = threadIdx.x; b < w * 3; b += blockDim.x) {
-        const int x = b / 3;
-        rs_dst(dst, img, y, x)[b - x * 3] = line[b];
+    const uint8_t* line = src + (static_cast<int64_t>(img) * h + y) * w * ps;
+    if (ps == 4) {  // RGBX source: one 32-bit load per pixel, three byte stores
+        const uint32_t* lw = reinterpret_cast<const uint32_t*>(line);
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            const uint32_t v = lw[x];
+            uint8_t* o = rs_dst(dst, img, y, x);
+            o[0] = v & 255; o[1] = (v >> 8) & 255; o[2] = (v >> 16) & 255;
+        }
+    } else {
+        for (int b = threadIdx.x; b < w * 3; b += blockDim.x) {
+            const int x = b / 3;
+            rs_dst(dst, img, y, x)[b - x * 3] = line[b];
+        }
     }
 }
 
 }  // namespace vr
 
-extern "C" int vr_resample_u8(const uint8_t* src, int32_t n, int32_t in_h, int32_t in_w, const int32_t* bounds_h,
+extern "C" int vr_resample_u8(const uint8_t* src, int32_t src_pixel_bytes, int32_t n, int32_t in_h, int32_t in_w,
+                              const int32_t* bounds_h,
                               const int32_t* coeffs_h, int32_t ksize_h, const int32_t* bounds_v, const int32_t* coeffs_v,
                               int32_t ksize_v, int32_t row_first, int32_t row_count, int32_t out_h, int32_t out_w,
                               uint8_t* tmp, uint8_t* out, const int32_t* first_cell, int32_t cell_h, int32_t cell_w,
@@ -161,39 +172,42 @@ extern "C" int vr_resample_u8(const uint8_t* src, int32_t n, int32_t in_h, int32
     VR_REQUIRE(!need_h || (coeffs_h && ksize_h > 0), "vr_resample_u8: horizontal pass needs coefficients");
     VR_REQUIRE(!need_v || (coeffs_v && ksize_v > 0), "vr_resample_u8: vertical pass needs coefficients");
     VR_REQUIRE(!(need_h && need_v) || tmp, "vr_resample_u8: two passes need the intermediate buffer");
-    VR_REQUIRE(in_w <= 16384, "vr_resample_u8: rows wider than 16384 pixels are not supported");
+    VR_REQUIRE(in_w <= 12288, "vr_resample_u8: rows wider than 12288 pixels are not supported");
+    const int ps = src_pixel_bytes;
+    VR_REQUIRE(ps == 3 || ps == 4, "vr_resample_u8: src_pixel_bytes must be 3 (RGB) or 4 (RGBX), got %d", ps);
+    VR_REQUIRE(ps == 3 || (reinterpret_cast<uintptr_t>(src) & 3) == 0, "vr_resample_u8: RGBX sources must be 4-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     RsDst cells{out, first_cell, 0, 0, cell_h, cell_w, out_w / cell_w};
     const int tmp_pitch = (out_w * 3 + 3) & ~3;  // rows of the intermediate start on 4-byte boundaries
     if (!need_h && !need_v) {
-        resample_copy_kernel<<<dim3(in_h, n), 256, 0, s>>>(src, in_h, in_w, cells);
+        resample_copy_kernel<<<dim3(in_h, n), 256, 0, s>>>(src, in_h, in_w, ps, cells);
         VR_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
     const uint8_t* vsrc = src;
-    int vrows = in_h, shift = 0, vpitch = in_w * 3;
+    int vrows = in_h, shift = 0, vpitch = in_w * ps, vps = ps;
     if (need_h) {
         // Pillow runs the horizontal pass over source rows [row_first, row_first + row_count) only (the rows the
         // vertical pass reads); with no vertical pass that is every row
         const int r0 = need_v ? row_first : 0, rc = need_v ? row_count : in_h;
         VR_REQUIRE(r0 >= 0 && rc > 0 && r0 + rc <= in_h, "vr_resample_u8: bad source row range [%d, %d)", r0, r0 + rc);
         RsDst hd = need_v ? RsDst{tmp, nullptr, rc, tmp_pitch, 0, 0, 0} : cells;
-        const size_t smem = static_cast<size_t>(RS_ROWS) * ((static_cast<size_t>(in_w) * 3 + 3) & ~size_t(3));
+        const size_t smem = static_cast<size_t>(RS_ROWS) * ((static_cast<size_t>(in_w) * ps + 3) & ~size_t(3));
         static bool smem_set = false;
         if (smem > 48 * 1024 && !smem_set) {
             VR_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             smem_set = true;
         }
-        resample_h_kernel<<<dim3((rc + RS_ROWS - 1) / RS_ROWS, n), 256, smem, s>>>(src, in_h, in_w, r0, rc, bounds_h, coeffs_h,
-                                                                                 out_w, hd);
+        resample_h_kernel<<<dim3((rc + RS_ROWS - 1) / RS_ROWS, n), 256, smem, s>>>(src, in_h, in_w, ps, r0, rc, bounds_h,
+                                                                                 coeffs_h, out_w, hd);
         VR_CHECK_CUDA(cudaGetLastError());
-        vsrc = tmp; vrows = rc; shift = r0; vpitch = tmp_pitch;
+        vsrc = tmp; vrows = rc; shift = r0; vpitch = tmp_pitch; vps = 3;
     }
     if (need_v) {
         if (need_h && (reinterpret_cast<uintptr_t>(tmp) & 3) == 0)
-            resample_v_kernel<true><<<dim3(out_h, n), 256, 0, s>>>(vsrc, vrows, out_w, vpitch, bounds_v, coeffs_v, ksize_v, shift, cells);
+            resample_v_kernel<true><<<dim3(out_h, n), 256, 0, s>>>(vsrc, vrows, out_w, vpitch, vps, bounds_v, coeffs_v, ksize_v, shift, cells);
         else
-            resample_v_kernel<false><<<dim3(out_h, n), 256, 0, s>>>(vsrc, vrows, out_w, vpitch, bounds_v, coeffs_v, ksize_v, shift, cells);
+            resample_v_kernel<false><<<dim3(out_h, n), 256, 0, s>>>(vsrc, vrows, out_w, vpitch, vps, bounds_v, coeffs_v, ksize_v, shift, cells);
         VR_CHECK_CUDA(cudaGetLastError());
     }
     return 0;

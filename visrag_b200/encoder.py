@@ -262,17 +262,17 @@ class VisRAGEngine:
             self._frontend = DeviceFrontEnd(self.device)
         by_size = {}
         for j in jobs:
-            by_size.setdefault(j.pixels.shape[:2], []).append(j)
-        for (H, W), lst in by_size.items():
-            pages = self._stage_slices([j.pixels for j in lst], (s, "page", (H, W)))
+            by_size.setdefault(j.pixels.shape, []).append(j)  # (H, W, 3 | 4): RGB and RGBX pages are stacked apart
+        for (H, W, ps), lst in by_size.items():
+            pages = self._stage_slices([j.pixels for j in lst], (s, "page", (H, W, ps)))
             plan = lst[0].plan  # a function of (W, H) only
             tkey = lst[0].thumb[0]
-            first = self._stage(np.asarray([j.thumb[1] for j in lst], dtype=np.int32), (s, "first_t", (H, W)))
+            first = self._stage(np.asarray([j.thumb[1] for j in lst], dtype=np.int32), (s, "first_t", (H, W, ps)))
             self._frontend.resize_into(pages, plan.source_size[0], plan.source_size[1], groups[tkey], first,
                                        plan.source_size[0], plan.source_size[1])
             if plan.grid is not None:
                 ckey = lst[0].cells[0]
-                first = self._stage(np.asarray([j.cells[1] for j in lst], dtype=np.int32), (s, "first_c", (H, W)))
+                first = self._stage(np.asarray([j.cells[1] for j in lst], dtype=np.int32), (s, "first_c", (H, W, ps)))
                 self._frontend.resize_into(pages, plan.refine_size[0], plan.refine_size[1], groups[ckey], first,
                                            plan.cell_size[0], plan.cell_size[1])
             pages.record_stream(torch.cuda.current_stream(self.device))

@@ -143,14 +143,14 @@ def _tokenize(content: str, tokenizer, max_inp_length: Optional[int]) -> Tuple[n
     return ids, bound
 
 
-MAX_DEVICE_PAGE_WIDTH = 16384  # vr_resample_u8 stages four source rows in shared memory
+MAX_DEVICE_PAGE_WIDTH = 12288  # vr_resample_u8 stages four source rows (up to 4 bytes per pixel) in shared memory
 
 
 @dataclass
 class PageJob:
     """A page whose slices the DEVICE front-end renders (frontend.DeviceFrontEnd): raw pixels + plan + where the
     results go (group key, index inside the group) for the thumbnail and for the first grid cell."""
-    pixels: np.ndarray                                   # uint8 [H,W,3]
+    pixels: np.ndarray                                   # uint8 [H,W,3] (RGB) or [H,W,4] (Pillow's RGBX rows)
     plan: SlicePlan
     thumb: Optional[Tuple[Tuple[int, int], int]] = None
     cells: Optional[Tuple[Tuple[int, int], int]] = None
@@ -208,11 +208,12 @@ def prepare_batch(texts: Sequence[str], images: Sequence, tokenizer, cfg: VisRAG
         if image:
             plan = plan_slices(image.size[0], image.size[1], cfg)
             content = placeholder_text(plan, tokenizer, cfg.query_num) + "\n" + text
-            # a page that needs no resampling (already thumbnail sized, no grid) gains nothing from the device path
-            resampled = plan.grid is not None or tuple(image.size) != tuple(plan.source_size)
-            if device_frontend and resampled and image.size[0] <= MAX_DEVICE_PAGE_WIDTH:
-                rgb = image.convert("RGB") if image.mode != "RGB" else image
-                return PageJob(np.ascontiguousarray(_rgb_array(rgb)), plan), content
+            # every page goes to the device as it is: Pillow's native RGBX rows when they can be exported zero-copy
+            # (frontend.page_pixels), so the host neither resamples nor repacks pixels
+            if device_frontend and image.size[0] <= MAX_DEVICE_PAGE_WIDTH:
+                from .frontend import page_pixels
+
+                return PageJob(page_pixels(image), plan), content
             return render_slices(image, plan), content
         return [], text
 

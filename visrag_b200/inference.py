@@ -16,6 +16,8 @@ import math
 import os
 import pathlib
 import pickle
+import sys
+import time
 from typing import Any, Dict, Iterable, List, Optional
 
 import numpy as np
@@ -52,14 +54,16 @@ def _split_batch(batch: dict, parts: int) -> List[dict]:
 
 
 @torch.no_grad()
-def encode_stream(batches: Iterable[dict], model, model_additional_args: Optional[dict] = None, ramp_parts: int = 4):
+def encode_stream(batches: Iterable[dict], model, model_additional_args: Optional[dict] = None, ramp_parts: int = 1):
     """Pipelined encode: yields (ids, float32 ndarray [n, d]) per batch, in order.
 
     Three things overlap: the host preparation of batch i+1 (PIL resampling, tokenisation; worker thread), the kernels
     of batch i (asynchronous launches on the current stream) and the device->host copy of batch i-1 (pinned buffer +
-    event instead of the reference's blocking `.cpu()`, `inference.py:98`). The FIRST batch is cut into `ramp_parts`
-    pieces so that the GPU starts after a fraction of a batch has been prepared instead of idling through the whole
-    first preparation (the pipeline fill); its pieces are re-joined before it is yielded."""
+    event instead of the reference's blocking `.cpu()`, `inference.py:98`). `ramp_parts` > 1 cuts the FIRST batch into
+    pieces (re-joined before it is yielded) so that the GPU starts after a fraction of a batch has been prepared. That
+    paid off while host preparation cost ~55 ms per 128 pages; with the zero-copy RGBX page path it costs ~4 ms, and
+    differently sized pieces make the caching allocator re-carve its blocks (a synchronising cudaFree/cudaMalloc:
+    measured 70 ms on the first full-size batch), so the default is no ramp."""
     from collections import deque
     from concurrent.futures import ThreadPoolExecutor
 
@@ -84,6 +88,7 @@ def encode_stream(batches: Iterable[dict], model, model_additional_args: Optiona
     def collect():
         ids, host, ev, last = pending.popleft()
         ev.synchronize()
+        mark(f"collected {len(ids)} items")
         joined_ids.extend(ids)
         joined.append(host.numpy().copy())
         if not last:
@@ -93,14 +98,23 @@ def encode_stream(batches: Iterable[dict], model, model_additional_args: Optiona
         joined.clear()
         return out
 
+    trace = os.environ.get("VR_TRACE_STREAM")
+    t_start = time.perf_counter()
+
+    def mark(what):
+        if trace:
+            print(f"[encode_stream +{(time.perf_counter() - t_start) * 1e3:7.1f} ms] {what}", file=sys.stderr, flush=True)
+
     with ThreadPoolExecutor(max_workers=1) as pool:
         fut = pool.submit(model.prepare, cur[0], **kw)
         while cur is not None:
             pb = fut.result()
+            mark(f"prepared {pb.n_items} items")
             nxt = next(it, None)
             if nxt is not None:
                 fut = pool.submit(model.prepare, nxt[0], **kw)
             reps = model.encode_prepared(pb)
+            mark("launched")
             host = torch.empty(reps.shape, dtype=torch.float32).pin_memory()
             host.copy_(reps, non_blocking=True)
             ev = torch.cuda.Event()
