@@ -97,6 +97,38 @@ def test_boundaries_against_oracle_on_fresh_inputs():
     assert cosine_rows(gt.cpu().numpy(), O.encode(sd, cfg, tok, qs[1:], [None], max_inp_length=40)).min() >= COS_MIN
 
 
+def test_vision_tower_and_resampler_against_oracle():
+    """One boundary further in than B1: ViT tokens (after the final LayerNorm) and the resampler's 64 x hidden output for
+    single slices of two geometries, against the oracle's fp32 towers on the same pixels. Tolerance 3e-2 relative to the
+    largest reference value (26 bf16 transformer blocks)."""
+    from PIL import Image
+
+    from oracle import restated as O
+    from visrag_b200 import host
+    from visrag_b200.encoder import VisRAGEngine
+    from visrag_b200.weights import random_state_dict
+
+    cfg, wseed, pages, _, _ = load_case("tiny_v1")
+    sd = random_state_dict(cfg, wseed)
+    eng = VisRAGEngine(cfg, sd)
+
+    def close(got, want, tol):
+        want = torch.as_tensor(want).float()
+        err = (got.float().cpu() - want).abs().max().item()
+        return err <= tol * max(want.abs().max().item(), 1.0) and bool(torch.isfinite(got.float()).all())
+
+    for img in (pages[0], pages[3]):
+        slices = host.render_slices(img, host.plan_slices(*img.size, cfg))
+        for s in slices[:2]:
+            tok = eng.vit_tokens(torch.from_numpy(s)[None].cuda())
+            want = O.vit_forward(sd, cfg, O.pixel_values(Image.fromarray(s)))
+            assert close(tok, want, 3e-2), s.shape
+            gh, gw = s.shape[0] // 14, s.shape[1] // 14
+            out = torch.empty(cfg.query_num, cfg.hidden, device="cuda")
+            eng.resample(tok, 1, gh, gw, out)
+            assert close(out, O.resampler_forward(sd, cfg, want, gh, gw), 3e-2), s.shape
+
+
 def test_batch_composition_does_not_change_results():
     """Same item alone vs inside a mixed batch: bit-identical (no padding, no cross-sequence leakage)."""
     from visrag_b200.config import VisRAGConfig

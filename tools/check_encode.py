@@ -206,74 +206,8 @@ def stage_attention_perf():
     return True
 
 
-def _tiny():
-    from tests.helpers import load_case
-    from visrag_b200.weights import random_state_dict
-
-    cfg, wseed, pages, queries, z = load_case("tiny_v1")
-    return cfg, random_state_dict(cfg, wseed), pages, queries, z
-
-
-def stage_vision():
-    import numpy as np
-    import torch
-    from oracle import restated as O
-    from visrag_b200 import host
-    from visrag_b200.encoder import VisRAGEngine
-
-    cfg, sd, pages, queries, z = _tiny()
-    eng = VisRAGEngine(cfg, sd)
-    ok = True
-    for img in (pages[0], pages[3]):
-        sl = host.render_slices(img, host.plan_slices(*img.size, cfg))
-        for s in sl[:2]:
-            px = torch.from_numpy(s)[None].cuda()
-            tok = eng.vit_tokens(px)
-            from PIL import Image
-
-            pil = Image.fromarray(s)
-            want = O.vit_forward(sd, cfg, O.pixel_values(pil))
-            ok &= report(f"vit tokens {s.shape}", tok, want, 3e-2)
-            gh, gw = s.shape[0] // 14, s.shape[1] // 14
-            out = torch.empty(64, cfg.hidden, device="cuda")
-            eng.resample(tok, 1, gh, gw, out)
-            want_r = O.resampler_forward(sd, cfg, want, gh, gw)
-            ok &= report(f"resampler {s.shape}", out, want_r, 3e-2)
-    return ok
-
-
-def stage_encode():
-    import numpy as np
-    import torch
-    from oracle import restated as O
-    from tests.helpers import cosine_rows
-    from visrag_b200.encoder import VisRAGEngine
-    from visrag_b200.tokenizer_stub import StubTokenizer
-
-    cfg, sd, pages, queries, z = _tiny()
-    eng = VisRAGEngine(cfg, sd)
-    tok = StubTokenizer(cfg.vocab)
-    p = eng.encode([""] * len(pages), pages, tok).cpu().numpy()
-    q = eng.encode(queries, [None] * len(queries), tok).cpu().numpy()
-    ok = True
-    cp, cq = cosine_rows(p, z["page_reps"]), cosine_rows(q, z["query_reps"])
-    print("page cosine vs reference golden:", np.round(cp, 5), flush=True)
-    print("query cosine vs reference golden:", np.round(cq, 5), flush=True)
-    ok &= bool((cp > 0.999).all() and (cq > 0.999).all())
-    S = q @ p.T
-    top = np.argsort(-S, axis=1)[:, : z["topk_indices"].shape[1]]
-    print("topk ours\n", top, "\nreference\n", z["topk_indices"], flush=True)
-    ok &= bool((np.sort(top, 1) == np.sort(z["topk_indices"], 1)).all())
-    # mixed batch in one call == separate calls
-    both = eng.encode([""] * 2 + queries[:2], pages[:2] + [None, None], tok).cpu().numpy()
-    ok &= report("mixed batch pages", torch.from_numpy(both[:2]), torch.from_numpy(p[:2]), 2e-2)
-    ok &= report("mixed batch queries", torch.from_numpy(both[2:]), torch.from_numpy(q[:2]), 2e-2)
-    print("norms", np.linalg.norm(p, axis=1), flush=True)
-    return ok
-
-
 STAGES = {"elementwise": stage_elementwise, "attention": stage_attention, "attention_v1": stage_attention_v1,
-          "attention_perf": stage_attention_perf, "vision": stage_vision, "encode": stage_encode}
+          "attention_perf": stage_attention_perf}
 
 if __name__ == "__main__":
     if len(sys.argv) == 2:
