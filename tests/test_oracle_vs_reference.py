@@ -56,3 +56,43 @@ def test_other_poolings_equal_reference_on_a_ragged_batch(pooling):
     ref = RS.encode(model, tok, items, False)
     got = O.encode(sd, cfg, tok, texts, images, pooling=pooling)
     assert np.abs(got - ref).max() < 2e-6, pooling
+
+
+def test_score_topk_and_run_files_equal_reference(tmp_path):
+    """The scoring side of the path against the REAL reference functions on the CPU: `_retrieve_one_shard`
+    (`retriever/dense_retriever.py:13-34`) on a pickle shard, `save_as_trec` / `load_from_trec` / `eval_mrr`
+    (`utils.py:125-175,285-308`). Random unit vectors: no score ties, so torch.topk's unspecified tie order cannot differ."""
+    import pickle
+
+    import torch
+
+    RS._import_reference()
+    from openmatch import utils as ref_utils
+    from openmatch.retriever.dense_retriever import _retrieve_one_shard as ref_retrieve
+
+    from oracle import restated as O
+    from visrag_b200 import inference as I
+    from visrag_b200 import retriever as R
+
+    rs = np.random.RandomState(12)
+    D = rs.randn(500, 64).astype(np.float32)
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+    Q = rs.randn(7, 64).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    lookup = [f"doc{i}" for i in range(len(D))]
+    shard = str(tmp_path / "embeddings.corpus.rank.0")
+    R.save_shard(shard, D, lookup)                      # our writer, the reference's reader
+    assert pickle.load(open(shard, "rb"))[1] == lookup
+    s_ref, i_ref, look_ref = ref_retrieve(shard, torch.from_numpy(Q), 10, "cpu")
+    s, i = O.score_topk(Q, D, 10)
+    assert look_ref == lookup and np.array_equal(i, i_ref.numpy()) and np.abs(s - s_ref.numpy()).max() < 1e-6
+    # run files and MRR: our functions and the reference's read each other's output and agree
+    run = {f"q{q}": {lookup[j]: float(s[q, r]) for r, j in enumerate(i[q])} for q in range(len(Q))}
+    qrel = {f"q{q}": {lookup[int(i[q, q % 10])]: 1} for q in range(len(Q))}
+    ours, theirs = str(tmp_path / "ours.trec"), str(tmp_path / "theirs.trec")
+    I.save_as_trec(run, ours)
+    ref_utils.save_as_trec(run, theirs)
+    assert open(ours).read() == open(theirs).read()
+    assert ref_utils.load_from_trec(ours) == I.load_from_trec(theirs)
+    assert ref_utils.eval_mrr(qrel, run, 10) == I.eval_mrr(qrel, run, 10)
+    assert ref_utils.eval_mrr(qrel, run, 3) == I.eval_mrr(qrel, run, 3)
