@@ -116,3 +116,22 @@ def test_page_pixels_exports_pillow_rows_without_repacking():
         px = F.page_pixels(im)
         assert px.dtype == np.uint8 and px.shape[:2] == (im.size[1], im.size[0]) and px.shape[2] in (3, 4)
         assert np.array_equal(px[..., :3], np.asarray(im.convert("RGB")))
+
+
+def test_page_pixels_on_decoded_files_and_multi_block_images():
+    """Lazily decoded PNG/JPEG files export the same way; images large enough for Pillow to allocate them in several
+    blocks cannot be exported as one buffer and must fall back to the packed RGB copy - with the same pixels."""
+    import io
+
+    rs = np.random.RandomState(2)
+    arr = rs.randint(0, 256, (120, 200, 3), dtype=np.uint8)
+    for fmt in ("PNG", "JPEG"):
+        buf = io.BytesIO()
+        Image.fromarray(arr).save(buf, format=fmt)
+        buf.seek(0)
+        im = Image.open(buf)
+        px = F.page_pixels(im)
+        assert np.array_equal(px[..., :3], np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")))
+    big = rs.randint(0, 256, (4200, 3300, 3), dtype=np.uint8)
+    px = F.page_pixels(Image.fromarray(big))
+    assert px.shape[:2] == (4200, 3300) and np.array_equal(px[..., :3], big)
