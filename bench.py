@@ -309,7 +309,7 @@ def run_ours(a):
             "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "queries": f"{nq} text queries top-10 over {nd * world} pages",
-                       "model": a.model, "pages_per_step_per_gpu": P, "global_batch": P * world, "patches_per_page": n_patches,
+                       "size": a.model, "pages_per_step_per_gpu": P, "global_batch": P * world, "patches_per_page": n_patches,
                        "lm_tokens_per_page": lm_tokens, "parallelism": f"dp{world} (pages sharded, no encode collective)",
                        "weights": "random-init, bf16", "l2": "working set (6.3 GB weights + >1 GB activations per step) >> 126 MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -417,7 +417,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "model": a.model, "pages_per_step_per_gpu": 1,
+        "config": {"workload": workload_name(a), "size": a.model, "pages_per_step_per_gpu": 1,
                    "sample": "each step is ONE page of the workload through the full model on the host cores"},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
