@@ -131,7 +131,9 @@ typedef struct {
 } vr_attn_params;
 
 int vr_attention(const vr_attn_params* p, void* stream);
-/* test hook: 0 = default, 1 = always use the one-tile-per-CTA kernel, 3 = experimental 64-key-block kernel */
+/* test / benchmark hook (process-wide): 0 = default dispatch, 1 = always the one-tile-per-CTA kernel,
+ * 3 = 64-key-block kernel with Q and P in tensor memory, 5 = two-tile kernel with Q in tensor memory as well
+ * (both measured slower than the default; kept as tested alternatives) */
 void vr_attention_force_v1(int32_t variant);
 
 
