@@ -1,8 +1,9 @@
 """Encode-path parity on the B200: CUDA engine (through the C ABI and the reference-signature classes) against
   (1) golden embeddings produced by the REAL reference (tests/golden/*.npz), tiny and full-size model,
   (2) the oracle restatement on freshly seeded inputs, at the B1 (hidden states) and B2 (embeddings) boundaries.
-Stated tolerance (north_star: "within a stated fp tolerance"): cosine(embedding, fp32 reference) >= 0.999 per vector
-and max |diff| <= 4e-3 on unit vectors; top-k id sets identical on the golden (query, corpus) sets. The engine computes
+Stated tolerance (north_star: "within a stated fp tolerance"): cosine(embedding, fp32 reference) >= 0.9999 per vector
+and max |diff| <= 1e-3 on unit vectors; ORDERED top-k ids identical to the reference's torch.topk on the golden
+(query, corpus) sets (k < n), Recall@1/5 equal with zero slack. The engine computes
 in bf16 operands / fp32 accumulate with fp32 residual streams; the reference run is fp32."""
 import numpy as np
 import pytest
@@ -12,7 +13,7 @@ from tests.helpers import QUERY_PREFIX, cosine_rows, load_case, synth_pages
 
 pytestmark = pytest.mark.gpu
 
-COS_MIN, ABS_MAX = 0.999, 4e-3
+COS_MIN, ABS_MAX = 0.9999, 1e-3
 
 
 def _engine_model(cfg, sd, pooling="wmean"):
@@ -43,8 +44,31 @@ def _check_case(name):
     assert np.abs(p - z["page_reps"]).max() <= ABS_MAX and np.abs(q - z["query_reps"]).max() <= ABS_MAX
     assert np.allclose(np.linalg.norm(p, axis=1), 1.0, atol=1e-5)
     k = z["topk_indices"].shape[1]
-    top = np.argsort(-(q @ p.T), axis=1)[:, :k]
-    assert np.array_equal(np.sort(top, 1), np.sort(z["topk_indices"], 1))
+    ref_top = z["topk_indices"]
+    if k >= len(pages):  # v1 goldens (k == n): only the id sets can be compared
+        top = np.argsort(-(q @ p.T), axis=1)[:, :k]
+        assert np.array_equal(np.sort(top, 1), np.sort(ref_top, 1))
+        return cp.min(), cq.min()
+    # ranking parity through the engine's own scorer (tensor-core filter + exact fp32 rescoring), k < n:
+    # the ORDERED top-k ids must equal the reference's torch.matmul + torch.topk (dense_retriever.py:25-30)
+    from visrag_b200 import retriever as R
+
+    s_run, i_run = R.score_topk(out.q_reps, R.build_index(out.p_reps), k)
+    i_run, s_run = i_run.cpu().numpy(), s_run.cpu().numpy()
+    print(f"{name}: cos pages >= {cp.min():.7f}, queries >= {cq.min():.7f}, max |score diff| "
+          f"{np.abs(s_run - z['topk_scores']).max():.2e}, golden min gap {float(z['min_gap']):.2e}")
+    assert np.array_equal(i_run, ref_top), (i_run, ref_top)
+    assert np.abs(s_run - z["topk_scores"]).max() <= 2 * ABS_MAX
+    # Recall@1/5 with zero slack: relevance = the reference's own best page per query, and for the two real
+    # (query, page) rows of the reference's parquet example the page that belongs to the query
+    from oracle import restated as O
+
+    relevant = [{int(ref_top[qi, 0])} for qi in range(len(queries))]
+    spec = [e.get("name") for e in __import__("json").loads(str(z["page_spec"]))]
+    for r, nm in enumerate(("parquet0", "parquet1")):
+        relevant[len(queries) - 2 + r].add(spec.index(nm))
+    for kk in (1, 5):
+        assert O.recall_at_k(i_run, relevant, kk) == O.recall_at_k(ref_top, relevant, kk)
     return cp.min(), cq.min()
 
 
@@ -52,9 +76,22 @@ def test_tiny_model_matches_reference_golden():
     _check_case("tiny_v1")
 
 
+def test_tiny_model_ranking_matches_reference_golden():
+    """36 pages (28 structured synthetic documents incl. 8 multi-slice, 4 noise pages, the reference's 4 real example
+    images) x 10 queries (8 synthetic + the 2 real parquet queries), top-5 of 36."""
+    _check_case("tiny_v2")
+
+
 def test_full_size_model_matches_reference_golden():
     """SigLIP-so400m (26 blocks) + Resampler + MiniCPM-2B (40 layers), 3.1 B parameters, vs the real reference's fp32 run."""
     _check_case("full_v1")
+
+
+def test_full_size_model_ranking_matches_reference_golden():
+    """The 3.1 B-parameter engine on a corpus where ranking can differ: the full_v2 golden (36 pages incl. 8 synthetic
+    multi-slice documents and the reference's own parquet pages + cat/dog photos, 10 queries, top-5 with k < n) was produced
+    by the REAL reference in fp32 (oracle/gen_golden.py --full-v2). Ordered ids identical, Recall@1/5 equal, cos >= 0.9999."""
+    _check_case("full_v2")
 
 
 def test_boundaries_against_oracle_on_fresh_inputs():

@@ -77,3 +77,21 @@ def test_score_topk_ties_short_corpus_and_merge():
     assert np.array_equal(mi, gi) and np.allclose(ms, gs)
     rel = [set(gi[q, :2].tolist()) for q in range(7)]
     assert O.recall_at_k(gi, rel, 5) == 1.0 and O.recall_at_k(gi[:, ::-1], rel, 1) < 1.0
+
+
+def test_oracle_reproduces_reference_ranking_on_the_document_corpus():
+    """tiny_v2: 36 pages (structured synthetic documents, noise pages and the reference's four real example images) x 10
+    queries through the REAL reference; the oracle must give the same embeddings and the same ORDERED top-5 of 36."""
+    cfg, wseed, pages, queries, z = load_case("tiny_v2")
+    assert len(pages) == 36 and len(queries) == 10 and z["topk_indices"].shape == (10, 5)
+    sd = random_state_dict(cfg, wseed)
+    tok = StubTokenizer(cfg.vocab)
+    p = O.encode(sd, cfg, tok, [""] * len(pages), pages)
+    q = O.encode(sd, cfg, tok, queries, [None] * len(queries))
+    assert np.abs(p - z["page_reps"]).max() < 2e-6 and np.abs(q - z["query_reps"]).max() < 2e-6
+    s, i = O.score_topk(q, p, 5)
+    assert np.array_equal(i, z["topk_indices"])
+    # the full-size golden shares the page spec and the queries (only the weights differ)
+    zf = np.load(f"{GOLDEN}/full_v2.npz")
+    assert str(zf["page_spec"]) == str(z["page_spec"]) and list(zf["queries"]) == list(z["queries"])
+    assert zf["page_reps"].shape == (36, 2304) and zf["topk_indices"].shape == (10, 5)
