@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VR_ABI_VERSION 1
+#define VR_ABI_VERSION 2
 
 typedef enum { VR_BF16 = 0, VR_F16 = 1, VR_F32 = 2 } vr_dtype;
 
@@ -128,10 +128,22 @@ typedef struct {
     int32_t causal;
     float scale;
     void* out; int64_t ldo;   /* bf16; row = cu_q ? cu_q[b]+i : b*max_q+i ; head h at column h*head_dim */
+    int32_t flags;            /* VR_ATTN_* */
 } vr_attn_params;
 
+/* The caller guarantees V[:, head_dim] == 1 for every head (head_dim == head_stride - 8; e.g. a bias of 1 in the zero
+ * padding of the QKV projection). Kernels that can use it take the softmax denominator out of the P.V MMA (column
+ * head_dim of the accumulator) instead of summing P in registers; the others ignore the column. Results are the same
+ * up to fp32 summation order. */
+#define VR_ATTN_V_ONES_COLUMN 1
+
 int vr_attention(const vr_attn_params* p, void* stream);
-/* test / benchmark hook (process-wide): 0 = default dispatch, 1 = always the one-tile-per-CTA kernel,
+/* Dispatch: non-causal sequences longer than 128 queries (the ViT) run the persistent kernel of attention4.cuh (one CTA per
+ * SM loops over (query-tile pair, head, sequence) items; P in its own TMEM buffer so Q.K^T of the next key block is issued
+ * while the exps of the current one run); causal long sequences the two-tile kernel of attention2.cuh; everything else
+ * the single-tile kernel.
+ * test / benchmark hook (process-wide): 0 = default dispatch, 1 = always the one-tile-per-CTA kernel, 2 = attention2 wherever
+ * attention4 is the default,
  * 3 = 64-key-block kernel with Q and P in tensor memory, 5 = two-tile kernel with Q in tensor memory as well
  * (both measured slower than the default; kept as tested alternatives) */
 void vr_attention_force_v1(int32_t variant);

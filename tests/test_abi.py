@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert len(syms) >= 15 and "vr_gemm" in syms and "vr_attention" in syms and "vr_score_filter" in syms
     for s in syms:
         assert getattr(lib, s) is not None
-    assert lib.vr_abi_version() == 1
+    assert lib.vr_abi_version() == 2
 
 
 def test_errors_are_status_codes_with_messages(lib):

@@ -108,19 +108,40 @@ def _stage_attention_body(torch, ops):
     ok = True
     dev = "cuda"
     # --- ViT style: heads x 72 padded to 80, non-causal, fixed N per slice
-    for (S, N, nh) in [(1, 128, 1), (1, 256, 2), (3, 1024, 4), (2, 1036, 16), (5, 130, 3)]:
+    # (the persistent kernel loops over work items: (40, 784, 16) gives every CTA several items incl. partial second tiles;
+    #  ones=True: V carries a ones column in its padding and the kernel takes the softmax denominator out of the P.V MMA)
+    for (S, N, nh, ones) in [(1, 128, 1, False), (1, 256, 2, False), (3, 1024, 4, True), (2, 1036, 16, False), (5, 130, 3, True),
+                             (40, 784, 16, True), (7, 300, 5, False), (33, 1024, 16, True)]:
         hd, hs = 72, 80
         qkv = torch.zeros(S * N, 3, nh, hs, device=dev)
         qkv[..., :hd] = torch.randn(S * N, 3, nh, hd, device=dev)
+        if ones:
+            qkv[:, 2, :, hd] = 1.0
         qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
         cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=dev)
         out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device=dev)
         ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
-                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out)
+                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out, v_ones_column=ones)
         torch.cuda.synchronize()
         x = qkv.view(S, N, 3, nh, hs)[..., :hd].permute(2, 0, 3, 1, 4)  # [3,S,nh,N,hd]
         want = _attn_ref(x[0], x[1], x[2], hd ** -0.5, False).permute(0, 2, 1, 3).reshape(S * N, nh * hd)
-        ok &= report(f"attn vit S={S} N={N} heads={nh}", out, want, 2e-2)
+        ok &= report(f"attn vit S={S} N={N} heads={nh} ones={ones}", out, want, 2e-2)
+    # --- non-causal var-len with head dim 64 (no padding column): ragged sequences, some shorter than one tile pair
+    for lens in ([300, 129, 1000, 128, 257, 512],):
+        nh, hd = 3, 64
+        H = nh * hd
+        T = sum(lens)
+        qkv = torch.randn(T, 3 * H, device=dev).bfloat16()
+        cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+        out = torch.zeros(T, H, dtype=torch.bfloat16, device=dev)
+        ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=H, v_col0=2 * H, head_stride=64, head_dim=64, heads=nh, batch=len(lens),
+                      cu_k=cu, max_k=max(lens), cu_q=cu, max_q=max(lens), causal=False, scale=hd ** -0.5, out=out)
+        torch.cuda.synchronize()
+        wants = []
+        for i, n in enumerate(lens):
+            x = qkv[cu[i]:cu[i + 1]].view(n, 3, nh, hd).permute(1, 2, 0, 3)
+            wants.append(_attn_ref(x[0], x[1], x[2], hd ** -0.5, False).permute(1, 0, 2).reshape(n, H))
+        ok &= report(f"attn non-causal var-len lens={lens}", out, torch.cat(wants), 2e-2)
     # --- growing row maxima: later key tiles carry much larger scores, which forces the lazy O rescale in TMEM
     for (S, N, nh) in [(2, 512, 2), (1, 1024, 3)]:
         hd, hs = 72, 80
@@ -128,11 +149,12 @@ def _stage_attention_body(torch, ops):
         qkv[..., :hd] = torch.randn(S * N, 3, nh, hd, device=dev)
         ramp = torch.linspace(0.2, 6.0, N, device=dev).repeat(S)[:, None, None]   # key scale grows with position
         qkv[:, 1, :, :hd] *= ramp
+        qkv[:, 2, :, hd] = 1.0 if S == 2 else 0.0
         qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
         cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=dev)
         out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device=dev)
         ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
-                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out)
+                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out, v_ones_column=(S == 2))
         torch.cuda.synchronize()
         x = qkv.view(S, N, 3, nh, hs)[..., :hd].permute(2, 0, 3, 1, 4)
         want = _attn_ref(x[0], x[1], x[2], hd ** -0.5, False).permute(0, 2, 1, 3).reshape(S * N, nh * hd)
@@ -185,12 +207,16 @@ def stage_attention_perf():
     qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
     cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device="cuda")
     out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device="cuda")
-    for force in (0, 5, 3, 1):
+    qkv1 = qkv.clone().view(S * N, 3, nh, hs)
+    qkv1[:, 2, :, hd] = 1.0
+    qkv1 = qkv1.view(S * N, 3 * nh * hs)
+    for force, ones in ((0, True), (0, False), (2, False), (1, False)):
         L.lib().vr_attention_force_v1(force)
+        src = qkv1 if ones else qkv
 
         def run():
-            ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
-                          batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out)
+            ops.attention(src, src, src, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
+                          batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out, v_ones_column=ones)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -201,7 +227,7 @@ def stage_attention_perf():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"attention variant {force}: {ms:.3f} ms  {4.0 * N * N * nh * hd * S / ms / 1e9:.1f} TFLOP/s (useful)", flush=True)
+        print(f"attention variant {force} ones_column={ones}: {ms:.3f} ms  {4.0 * N * N * nh * hd * S / ms / 1e9:.1f} TFLOP/s (useful)", flush=True)
     L.lib().vr_attention_force_v1(0)
     return True
 

@@ -51,8 +51,11 @@ class AttnParams(C.Structure):
         ("max_q", C.c_int32), ("max_k", C.c_int32),
         ("causal", C.c_int32), ("scale", C.c_float),
         ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("flags", C.c_int32),
     ]
 
+
+VR_ATTN_V_ONES_COLUMN = 1
 
 _lib: Optional[C.CDLL] = None
 

@@ -3,6 +3,7 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
+#include "attention4.cuh"
 
 namespace vr {
 
@@ -32,6 +33,27 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.ldo = p.ldo;
     a.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
     a.ldq = p.ldq;
+    if constexpr (V2 && !CAUSAL) {
+        if (g_variant == 0) {
+            // default for long non-causal sequences (the ViT): persistent decoupled kernel, attention4.cuh
+            using Cfg4 = Att4Cfg<HS>;
+            const bool ones = (p.flags & VR_ATTN_V_ONES_COLUMN) != 0;
+            const int nqp = (p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM);
+            const long long items = static_cast<long long>(nqp) * p.heads * p.batch;
+            auto kern = ones ? attention4_tcgen05_kernel<HS, true> : attention4_tcgen05_kernel<HS, false>;
+            int dev = 0;
+            VR_CHECK_CUDA(cudaGetDevice(&dev));
+            static bool attr_set4[2][64] = {};
+            if (dev < 64 && !attr_set4[ones][dev]) {
+                VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
+                attr_set4[ones][dev] = true;
+            }
+            const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
+            kern<<<grid, ATT4_THREADS, Cfg4::SMEM_BYTES, stream>>>(maps, a, static_cast<int>(items), nqp);
+            VR_CHECK_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     if constexpr (V2) {
         if (g_variant == 3) {
             // experimental: 64-key blocks, double-buffered S / P in shared memory (attention3.cuh)
@@ -85,7 +107,8 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
 
 }  // namespace vr
 
-// test hook: 0 = default kernels, 1 = force the single-tile kernel for every shape, 3 = experimental attention3 kernel,
+// test hook: 0 = default kernels, 1 = force the single-tile kernel for every shape, 2 = round-1 two-tile kernel (attention2)
+// where the persistent attention4 kernel is the default, 3 = experimental attention3 kernel,
 // 5 = two-tile kernel with Q in tensor memory too (slower; kept as a measured alternative)
 extern "C" void vr_attention_force_v1(int32_t variant) { vr::g_variant = variant; }
 
@@ -97,6 +120,9 @@ extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
     VR_REQUIRE(p->head_dim <= p->head_stride && p->head_dim % 8 == 0, "vr_attention: head_dim %d vs stride %d",
                p->head_dim, p->head_stride);
     VR_REQUIRE(p->ldo % 8 == 0, "vr_attention: ldo must be a multiple of 8");
+    VR_REQUIRE(!(p->flags & VR_ATTN_V_ONES_COLUMN) || p->head_dim == p->head_stride - 8,
+               "vr_attention: VR_ATTN_V_ONES_COLUMN needs head_dim == head_stride - 8 (got %d / %d)", p->head_dim, p->head_stride);
+    VR_REQUIRE(static_cast<long long>(p->heads) * p->batch * ((p->max_q + 255) / 256) < (1ll << 31), "vr_attention: too many work items");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const bool c = p->causal != 0;
     const bool v2 = p->max_q > ATT_BM && g_variant != 1;  // more than one query tile per sequence

@@ -71,6 +71,8 @@ class VisRAGEngine:
                 bpad = torch.zeros((3, nh, hs), device=wq.device)
                 wpad[:, :, :hd] = wq
                 bpad[:, :, :hd] = bq
+                bpad[2, :, hd] = 1.0  # V[:, 72] == 1 for every head: the attention kernel reads the softmax denominator
+                #                       out of the P.V accumulator (VR_ATTN_V_ONES_COLUMN); Q/K padding stays zero
                 self.blocks.append(dict(
                     n1w=_f32(sd[p + "norm1.weight"], dev), n1b=_f32(sd[p + "norm1.bias"], dev),
                     qkv_w=_bf16(wpad.reshape(3 * nh * hs, D), dev), qkv_b=_f32(bpad.reshape(-1), dev),
@@ -155,7 +157,7 @@ class VisRAGEngine:
             ops.gemm(y, blk["qkv_w"], bias=blk["qkv_b"], out=qkv)
             ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * VIT_HEAD_STRIDE, v_col0=2 * nh * VIT_HEAD_STRIDE,
                           head_stride=VIT_HEAD_STRIDE, head_dim=cfg.vit_head_dim, heads=nh, batch=S, cu_k=cu, max_k=N,
-                          cu_q=cu, max_q=N, causal=False, scale=scale, out=att)
+                          cu_q=cu, max_q=N, causal=False, scale=scale, out=att, v_ones_column=True)
             ops.gemm(att, blk["proj_w"], bias=blk["proj_b"], resid=x, out=x, out_dtype=torch.float32)
             y = ops.layernorm(x, blk["n2w"], blk["n2b"], cfg.ln_eps)
             y = ops.gemm(y, blk["fc1_w"], bias=blk["fc1_b"], gelu=True)

@@ -113,7 +113,7 @@ def gemm(
 def attention(
     q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, q_col0: int, k_col0: int, v_col0: int, head_stride: int,
     head_dim: int, heads: int, batch: int, cu_k: torch.Tensor, max_k: int, cu_q: Optional[torch.Tensor], max_q: int,
-    causal: bool, scale: float, out: torch.Tensor,
+    causal: bool, scale: float, out: torch.Tensor, v_ones_column: bool = False,
 ) -> torch.Tensor:
     """softmax(QK^T*scale)V on tcgen05; q/k/v are bf16 token matrices (see include/visrag_b200.h)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
@@ -130,6 +130,7 @@ def attention(
     p.max_q, p.max_k = max_q, max_k
     p.causal, p.scale = int(causal), float(scale)
     p.out, p.ldo = out.data_ptr(), out.stride(0)
+    p.flags = L.VR_ATTN_V_ONES_COLUMN if v_ones_column else 0
     _launch("attention", 0.0, L.lib().vr_attention, C.byref(p), L.stream_ptr())
     return out
 
