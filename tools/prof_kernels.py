@@ -16,12 +16,15 @@ if what == "attn":
     N, nh, hd, hs = 1024, 16, 72, 80
     qkv = torch.zeros(S * N, 3, nh, hs, device=dev)
     qkv[..., :hd] = torch.randn(S * N, 3, nh, hd, device=dev)
+    ones = os.environ.get("PROF_ONES", "1") == "1"
+    if ones:
+        qkv[:, 2, :, hd] = 1.0
     qkv = qkv.reshape(S * N, 3 * nh * hs).bfloat16()
     cu = torch.arange(0, (S + 1) * N, N, dtype=torch.int32, device=dev)
     out = torch.zeros(S * N, nh * hd, dtype=torch.bfloat16, device=dev)
     for _ in range(3):
         ops.attention(qkv, qkv, qkv, q_col0=0, k_col0=nh * hs, v_col0=2 * nh * hs, head_stride=hs, head_dim=hd, heads=nh,
-                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out)
+                      batch=S, cu_k=cu, max_k=N, cu_q=cu, max_q=N, causal=False, scale=hd ** -0.5, out=out, v_ones_column=ones)
     torch.cuda.synchronize()
 else:
     M = S * 1024

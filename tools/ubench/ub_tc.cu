@@ -136,6 +136,47 @@ __global__ void __launch_bounds__(128, 1) k_mix(int a_fmt, int b_fmt, uint32_t a
     if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tm); }
 }
 
+// 7. hand-off latencies: (a) tcgen05.commit with nothing pending -> own mbarrier wait; (b) warp-to-warp ping-pong through
+//    mbarrier.arrive / try_wait; (c) the same with tcgen05.commit on one side (the issuer's side of the attention pipeline)
+__global__ void __launch_bounds__(128, 1) k_handoff(int mode, int reps, Res* out) {
+    __shared__ uint64_t bar_a, bar_b;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&bar_a, 1); mbar_init(&bar_b, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<32>(&slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    long long t0 = clock64();
+    if (mode == 0) {
+        if (warp == 0) {
+            for (int r = 0; r < reps; ++r) {
+                if (elect_one()) umma_commit(&bar_a);
+                __syncwarp();
+                mbar_wait(&bar_a, r & 1);
+            }
+        }
+    } else {
+        // warp 0: arrive A (plain or commit), wait B.   warp 1: wait A, arrive B
+        for (int r = 0; r < reps; ++r) {
+            if (warp == 0) {
+                if (mode == 1) { if (lane == 0) mbar_arrive(&bar_a); }
+                else { if (elect_one()) umma_commit(&bar_a); }
+                __syncwarp();
+                mbar_wait(&bar_b, r & 1);
+            } else if (warp == 1) {
+                mbar_wait(&bar_a, r & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_b);
+            }
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out->mma_cycles = t1 - t0;
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<32>(slot);
+}
+
 int main() {
     Res* d; Res h;
     CK(cudaMalloc(&d, sizeof(Res)));
@@ -170,6 +211,16 @@ int main() {
             CK(cudaMemcpy(&h, d, sizeof(Res), cudaMemcpyDeviceToHost));
             printf("  %s %d warps: %.2f cycles per warp-instruction on its SMSP\n", f16 ? "f16x2" : "f32  ", warps, h.mma_cycles / (512.0 * 8) / (warps / 4));
         }
+    printf("== 7. hand-off latency (cycles per round)\n");
+    for (int mode = 0; mode < 3; ++mode) {
+        CK(cudaMemset(d, 0, sizeof(Res)));
+        k_handoff<<<1, 128>>>(mode, 1000, d);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(&h, d, sizeof(Res), cudaMemcpyDeviceToHost));
+        const char* names[3] = {"tcgen05.commit (nothing pending) -> own wait", "ping-pong arrive/wait between two warps (round trip)",
+                                "ping-pong with tcgen05.commit on one side (round trip)"};
+        printf("  %s: %.0f\n", names[mode], h.mma_cycles / 1000.0);
+    }
     printf("== 6. kind::f16 operand type mix (A in TMEM x B in smem), expect 16*a*b\n");
     struct { int af, bf; uint32_t ab, bb; const char* name; float expect; } cases[] = {
         {1, 1, 0x3f803f80u, 0x40404040u, "A bf16 1.0 x B bf16 3.0", 48.f},

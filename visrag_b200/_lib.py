@@ -74,6 +74,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vr_attention.argtypes = [C.POINTER(AttnParams), vp]
     lib.vr_attention_force_v1.restype = None
     lib.vr_attention_force_v1.argtypes = [i32]
+    lib.vr_attention_set_trace.restype = None
+    lib.vr_attention_set_trace.argtypes = [vp, i32]
     lib.vr_im2col_norm.restype = i32
     lib.vr_im2col_norm.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp]
     lib.vr_layernorm.restype = i32
@@ -134,6 +136,51 @@ def ptr(t) -> Optional[int]:
 
 
 def stream_ptr() -> int:
+    """The CURRENT device's current stream. Kernels must be launched with the device that owns their buffers current:
+    every public entry point (engine, retriever, knowledge base) enters `on_device(...)`, and the op wrappers refuse tensors
+    of another device (`check_device`) instead of launching on the wrong GPU."""
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+def norm_device(device):
+    """torch.device with an explicit index ('cuda' -> the current device)."""
+    import torch
+
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise ValueError(f"visrag_b200 runs on CUDA devices only (got {d})")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+class on_device:
+    """Context manager: make `device` current (cudaSetDevice) for the launches inside; no-op when it already is."""
+
+    def __init__(self, device):
+        self.idx = norm_device(device).index
+        self.prev = None
+
+    def __enter__(self):
+        import torch
+
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            import torch
+
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def check_device(t) -> None:
+    import torch
+
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"visrag_b200: tensor lives on cuda:{t.device.index} but cuda:{torch.cuda.current_device()} is current; "
+                           "wrap the call in `with visrag_b200._lib.on_device(tensor.device):` (the engine / retriever entry points do)")

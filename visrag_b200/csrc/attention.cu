@@ -8,6 +8,8 @@
 namespace vr {
 
 static int g_variant = 0;  // see vr_attention_force_v1()
+static unsigned long long* g_trace = nullptr;  // see vr_attention_set_trace()
+static int g_trace_cap = 0;
 
 template <int HS, bool CAUSAL, bool V2>
 static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
@@ -33,6 +35,8 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.ldo = p.ldo;
     a.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
     a.ldq = p.ldq;
+    a.trace = g_trace;
+    a.trace_cap = g_trace_cap;
     if constexpr (V2 && !CAUSAL) {
         if (g_variant == 0) {
             // default for long non-causal sequences (the ViT): persistent decoupled kernel, attention4.cuh
@@ -41,13 +45,9 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
             const int nqp = (p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM);
             const long long items = static_cast<long long>(nqp) * p.heads * p.batch;
             auto kern = ones ? attention4_tcgen05_kernel<HS, true> : attention4_tcgen05_kernel<HS, false>;
-            int dev = 0;
-            VR_CHECK_CUDA(cudaGetDevice(&dev));
-            static bool attr_set4[2][64] = {};
-            if (dev < 64 && !attr_set4[ones][dev]) {
+            static unsigned long long attr_set4[2] = {0, 0};
+            if (first_use_on_device(&attr_set4[ones]))
                 VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES));
-                attr_set4[ones][dev] = true;
-            }
             const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
             kern<<<grid, ATT4_THREADS, Cfg4::SMEM_BYTES, stream>>>(maps, a, static_cast<int>(items), nqp);
             VR_CHECK_CUDA(cudaGetLastError());
@@ -67,11 +67,9 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
                 if (int rc = make_tmap_2d(&m3.v16, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 16, 32, true)) return rc;
             }
             auto kern = attention3_tcgen05_kernel<HS, CAUSAL>;
-            static bool attr_set3 = false;
-            if (!attr_set3) {
+            static unsigned long long attr_set3 = 0;
+            if (first_use_on_device(&attr_set3))
                 VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
-                attr_set3 = true;
-            }
             dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
             kern<<<grid, ATT3_THREADS, Cfg3::SMEM_BYTES, stream>>>(m3, a);
         } else {
@@ -83,21 +81,17 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
             const bool q_tmem = g_variant == 5 && p.ldq % 8 == 0 && p.q_col0 % 8 == 0 &&
                                 (reinterpret_cast<uintptr_t>(p.q) & 15) == 0;
             auto kern = q_tmem ? attention2_tcgen05_kernel<HS, CAUSAL, true> : attention2_tcgen05_kernel<HS, CAUSAL, false>;
-            static bool attr_set[2] = {false, false};
-            if (!attr_set[q_tmem]) {
+            static unsigned long long attr_set[2] = {0, 0};
+            if (first_use_on_device(&attr_set[q_tmem]))
                 VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-                attr_set[q_tmem] = true;
-            }
             dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
             kern<<<grid, ATT2_THREADS, Cfg2::SMEM_BYTES, stream>>>(maps, a);
         }
     } else {
         auto kern = attention_tcgen05_kernel<HS, CAUSAL>;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned long long attr_set = 0;
+        if (first_use_on_device(&attr_set))
             VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-            attr_set = true;
-        }
         dim3 grid((p.max_q + ATT_BM - 1) / ATT_BM, p.heads, p.batch);
         kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, a);
     }
@@ -111,6 +105,12 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
 // where the persistent attention4 kernel is the default, 3 = experimental attention3 kernel,
 // 5 = two-tile kernel with Q in tensor memory too (slower; kept as a measured alternative)
 extern "C" void vr_attention_force_v1(int32_t variant) { vr::g_variant = variant; }
+
+// debug hook: CTA 0 of the persistent kernel records (event, clock64) pairs per warp into `buf` ([12][cap] uint64; NULL = off)
+extern "C" void vr_attention_set_trace(void* buf, int32_t cap) {
+    vr::g_trace = reinterpret_cast<unsigned long long*>(buf);
+    vr::g_trace_cap = buf ? cap : 0;
+}
 
 extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
     using namespace vr;

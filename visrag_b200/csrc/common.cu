@@ -15,17 +15,29 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int current_device() {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    static int cached[64] = {};
+    const int dev = current_device();
+    const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+    if (cached[slot] == 0) {
+        int n = 0;
+        cached[slot] = (dev >= 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
     }
-    return cached;
+    return cached[slot];
+}
+
+bool first_use_on_device(unsigned long long* mask) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) return true;  // unknown device: redo the setup every time (correct, only slower)
+    const unsigned long long bit = 1ull << dev;
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

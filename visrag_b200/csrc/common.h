@@ -10,7 +10,11 @@
 namespace vr {
 
 void set_error(const char* fmt, ...);
-int num_sms();
+int current_device();  // cudaGetDevice, -1 on failure
+int num_sms();         // SM count of the CURRENT device (cached per device)
+// Per-device one-time setup (cudaFuncSetAttribute and the occupancy queries are per device, the library is per process):
+// returns true the first time it is called with `mask` while a given device is current. One mask per kernel instantiation.
+bool first_use_on_device(unsigned long long* mask);
 
 // 2-D row-major tensor [rows, cols] of 2-byte elements, box = [box_rows, box_cols].
 // swizzle_bytes in {0 (none / 16B interleave), 32, 64, 128}; box_cols*2 must be <= swizzle span.

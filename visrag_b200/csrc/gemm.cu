@@ -16,11 +16,9 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
     if (int rc = make_tmap_2d(SWAP ? &tb : &ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, bf16)) return rc;
     if (int rc = make_tmap_2d(SWAP ? &ta : &tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, bf16)) return rc;
     auto kern = gemm_tcgen05_kernel<BN, MODE, OUT_F32, GELU, AB_FMT, SWAP>;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;  // per template instantiation, one bit per device
+    if (first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
     const int tiles = SWAP ? ((g.N + GEMM_BM - 1) / GEMM_BM) * ((g.M + BN - 1) / BN)
                            : ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -36,16 +34,16 @@ static int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, 
     if (int rc = make_tmap_2d(&ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, true)) return rc;
     if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, true)) return rc;
     auto kern = gemm2_tcgen05_kernel<MODE, OUT_F32, GELU>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
     const int tiles = ((g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((g.N + Cfg::BN - 1) / Cfg::BN);
     // A persistent kernel must not launch more clusters than can be co-resident: GPCs with an odd number of usable SMs
     // cannot pair all of them, and a cluster that has to wait for a free pair would run its whole tile list after the
     // others finished (measured: 74 clusters requested -> about half the throughput). Ask the driver.
-    static int max_pairs = 0;
+    static int max_pairs_dev[64] = {};
+    const int dev_slot = (current_device() >= 0 && current_device() < 64) ? current_device() : 0;
+    int& max_pairs = max_pairs_dev[dev_slot];
     if (max_pairs == 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() / 2 * 2);

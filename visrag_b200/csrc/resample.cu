@@ -193,11 +193,9 @@ extern "C" int vr_resample_u8(const uint8_t* src, int32_t src_pixel_bytes, int32
         VR_REQUIRE(r0 >= 0 && rc > 0 && r0 + rc <= in_h, "vr_resample_u8: bad source row range [%d, %d)", r0, r0 + rc);
         RsDst hd = need_v ? RsDst{tmp, nullptr, rc, tmp_pitch, 0, 0, 0} : cells;
         const size_t smem = static_cast<size_t>(RS_ROWS) * ((static_cast<size_t>(in_w) * ps + 3) & ~size_t(3));
-        static bool smem_set = false;
-        if (smem > 48 * 1024 && !smem_set) {
+        static unsigned long long smem_set = 0;
+        if (smem > 48 * 1024 && first_use_on_device(&smem_set))
             VR_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            smem_set = true;
-        }
         resample_h_kernel<<<dim3((rc + RS_ROWS - 1) / RS_ROWS, n), 256, smem, s>>>(src, in_h, in_w, ps, r0, rc, bounds_h,
                                                                                  coeffs_h, out_w, hd);
         VR_CHECK_CUDA(cudaGetLastError());

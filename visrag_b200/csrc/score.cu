@@ -310,6 +310,9 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, lo
                           sqrtf(static_cast<float>(dim)) * 5.9604645e-8f * (sh_qnorm + dn) + 1e-6f;
         int flag = 0;
         if (sh_bound > -INFINITY && !(sh_bound + eps < kth)) flag = 1;  // something was dropped that might belong
+        // the bound assumes finite fp16 copies of both operands: a row norm >= 65504 (or inf / NaN, for which the
+        // comparison is false as well) means some |x| may have overflowed fp16 -> rerun this query through the fp32 scan
+        if (!(sh_qnorm < 65504.f) || !(dn < 65504.f)) flag = 1;
         flags[q] = flag;
     }
 }
@@ -477,11 +480,9 @@ extern "C" int vr_score_filter(const void* q_f16, int32_t nq, const void* d_f16,
     CUtensorMap tq, td;
     if (int rc = make_tmap_2d(&tq, q_f16, nq, dim, dim, GEMM_BM, GEMM_BK, 128, false)) return rc;
     if (int rc = make_tmap_2d(&td, d_f16, nd, dim, dim, 128, GEMM_BK, 128, false)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
     ScoreArgs g;
     g.nq = nq; g.nd = nd; g.dim = dim; g.ranges = ranges; g.cand_scores = cand_scores; g.cand_ids = cand_ids;
     dim3 grid(ranges, (nq + GEMM_BM - 1) / GEMM_BM);
@@ -499,11 +500,9 @@ extern "C" int vr_score_rescore(const float* q_f32, int32_t nq, const float* d_f
     const int lists = ranges * 2;
     const size_t smem = (static_cast<size_t>(dim) + static_cast<size_t>(lists) * SC_KT) * sizeof(float);
     VR_REQUIRE(smem <= 200 * 1024, "vr_score_rescore: candidate set too large for shared memory (%zu bytes)", smem);
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
+    static unsigned long long attr_set = 0;
+    if (smem > 48 * 1024 && first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_smem = 200 * 1024;
-    }
     rescore_topk_kernel<<<nq, RS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         q_f32, d_f32, nd, dim, lists, cand_scores, cand_ids, max_doc_norm, k, id_offset, out_scores,
         reinterpret_cast<long long*>(out_ids), flags);
@@ -517,11 +516,9 @@ extern "C" int vr_score_exact(const float* q_f32, int32_t nq, const float* d_f32
     VR_REQUIRE(nq > 0 && nd > 0 && dim % 4 == 0, "vr_score_exact: bad shape");
     const size_t smem = static_cast<size_t>(EX_QB) * dim * sizeof(float);
     VR_REQUIRE(smem <= 200 * 1024, "vr_score_exact: dim too large");
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    static unsigned long long attr_set = 0;
+    if (smem > 48 * 1024 && first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
     long long bx = (nd + 7) / 8;
     const long long cap = static_cast<long long>(num_sms()) * 4;
     if (bx > cap) bx = cap;

@@ -11,6 +11,7 @@ Every kernel is a C-ABI call (visrag_b200/ops.py); torch only owns the buffers.
 """
 from __future__ import annotations
 
+import functools
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -34,8 +35,20 @@ def _f32(t: torch.Tensor, dev) -> torch.Tensor:
     return t.to(device=dev, dtype=torch.float32).contiguous()
 
 
+def _on_own_device(fn):
+    """Run a VisRAGEngine method with the engine's device current (kernels launch on the current device's stream)."""
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with L.on_device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 class VisRAGEngine:
-    """Holds device weights in kernel-ready layouts and runs the encode pipeline."""
+    """Holds device weights in kernel-ready layouts and runs the encode pipeline. Every public method makes the engine's
+    own device current for its launches, so an engine on cuda:1 works while cuda:0 is the process's current device."""
 
     def __init__(self, cfg: VisRAGConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
                  max_vit_tokens: int = 131072, device_frontend: bool = True):
@@ -45,8 +58,12 @@ class VisRAGEngine:
         # True: pages travel as raw RGB and are resampled / cut into slices on the GPU (bit-identical to PIL,
         # frontend.py); False: PIL renders the slices on the host as the reference does
         self.device_frontend = device_frontend
-        self.device = torch.device(device)
+        self.device = L.norm_device(device)
         self.max_vit_tokens = max_vit_tokens
+        with L.on_device(self.device):
+            self._load(cfg, state_dict)
+
+    def _load(self, cfg: VisRAGConfig, state_dict: Dict[str, torch.Tensor]) -> None:
         sd, dev = state_dict, self.device
         D, E, H, I = cfg.vit_dim, cfg.hidden, cfg.hidden, cfg.inter
         nh, hd, hs = cfg.vit_heads, cfg.vit_head_dim, VIT_HEAD_STRIDE
@@ -139,6 +156,7 @@ class VisRAGEngine:
         return self._sincos_cache[key]
 
     # ------------------------------------------------------------------------------------------ vision
+    @_on_own_device
     def vit_tokens(self, pixels: torch.Tensor) -> torch.Tensor:
         """uint8 [S,h,w,3] (device) -> final-LayerNorm ViT tokens bf16 [S*N, D]."""
         cfg = self.cfg
@@ -164,6 +182,7 @@ class VisRAGEngine:
             ops.gemm(y, blk["fc2_w"], bias=blk["fc2_b"], resid=x, out=x, out_dtype=torch.float32)
         return ops.layernorm(x, self.vnorm_w, self.vnorm_b, cfg.ln_eps)
 
+    @_on_own_device
     def resample(self, tokens: torch.Tensor, S: int, gh: int, gw: int, out: torch.Tensor) -> None:
         """ViT tokens bf16 [S*N, D] -> 64 query tokens per slice, written to fp32 `out` [S*64, E]."""
         cfg = self.cfg
@@ -180,6 +199,7 @@ class VisRAGEngine:
         o = ops.layernorm(o, self.rs_lnpost[0], self.rs_lnpost[1], 1e-6)
         ops.gemm(o, self.rs_projT, out=out, out_dtype=torch.float32)
 
+    @_on_own_device
     def encode_vision(self, groups: Dict[Tuple[int, int], torch.Tensor], group_row0: Dict[Tuple[int, int], int],
                       n_slices: int) -> Optional[torch.Tensor]:
         """All slices of a batch -> fp32 [n_slices*64, E] (slice i occupies rows 64i..64i+63)."""
@@ -198,6 +218,7 @@ class VisRAGEngine:
         return out
 
     # ------------------------------------------------------------------------------------------ LM
+    @_on_own_device
     def lm_hidden(self, token_src: torch.Tensor, positions: torch.Tensor, cu: torch.Tensor, max_len: int,
                   vision: Optional[torch.Tensor]) -> torch.Tensor:
         """Packed decoder: returns the fp32 residual stream BEFORE the final RMSNorm, [T, H]."""
@@ -279,6 +300,7 @@ class VisRAGEngine:
                                            plan.cell_size[0], plan.cell_size[1])
             pages.record_stream(torch.cuda.current_stream(self.device))
 
+    @_on_own_device
     def upload(self, pb: PreparedBatch):
         """Host -> device copies of one prepared batch. Pinned staging is double buffered and the copies run on a
         dedicated copy stream, so batch i+1 travels over PCIe while batch i's kernels run; the compute stream only
@@ -305,6 +327,7 @@ class VisRAGEngine:
             t.record_stream(compute)  # allocated on the copy stream, consumed (and later freed) under the compute stream
         return out
 
+    @_on_own_device
     def encode_device(self, groups, group_row0, n_slices: int, src, pos, cu, max_len: int, pooling: str = "wmean",
                       normalize: bool = True, return_hidden: bool = False):
         """Inputs already in HBM -> pooled embeddings [B, hidden] fp32 (the device-resident hot path)."""
@@ -313,6 +336,7 @@ class VisRAGEngine:
         reps = ops.pool_norm(h, self.final_w, self.cfg.rms_eps, cu, pooling, normalize)
         return (reps, h) if return_hidden else reps
 
+    @_on_own_device
     def encode_prepared(self, pb: PreparedBatch, pooling: str = "wmean", normalize: bool = True,
                         return_hidden: bool = False):
         if pb.n_items == 0:
@@ -323,6 +347,7 @@ class VisRAGEngine:
         return self.encode_device(groups, pb.group_row0, pb.n_slices, src, pos, cu, int(pb.seq_lens.max()), pooling,
                                   normalize, return_hidden)
 
+    @_on_own_device
     def encode(self, texts: Sequence[str], images: Sequence, tokenizer, max_inp_length: Optional[int] = 2048,
                pooling: str = "wmean", normalize: bool = True) -> torch.Tensor:
         """(texts, PIL images | None) -> fp32 device tensor [B, hidden], L2-normalised."""

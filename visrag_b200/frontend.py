@@ -101,6 +101,7 @@ class DeviceFrontEnd:
         from . import _lib as L
 
         n, H, W, ps = pages.shape
+        L.check_device(pages)  # the engine's upload() enters its own device before calling this
         h = self._axis(W, out_w, True)
         v = self._axis(H, out_h, False)
         tmp = None

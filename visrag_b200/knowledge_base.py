@@ -57,7 +57,7 @@ class KnowledgeBase:
         """query_reps [nq, d] (tensor or ndarray, fp32) -> (scores [nq,k] f32, page indices [nq,k] i64) on the device."""
         q = query_reps if isinstance(query_reps, torch.Tensor) else torch.from_numpy(np.asarray(query_reps, dtype=np.float32))
         q = q.to(self.index.emb.device, torch.float32).reshape(-1, self.index.emb.shape[1]).contiguous()
-        return retriever.score_topk(q, self.index, min(topk, len(self)))
+        return retriever.score_topk(q, self.index, min(topk, len(self)))  # enters the index's device itself
 
     def retrieve(self, query_rep, topk: int) -> List[str]:
         """`answer.py: retrieve` after the query is encoded: paths of the top-k page images, best first."""

@@ -44,6 +44,7 @@ def _launch(kind: str, flops: float, fn, *args) -> None:
 def _bf16_2d(t: torch.Tensor, name: str) -> None:
     if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
         raise ValueError(f"{name}: expected a CUDA bf16 matrix with unit inner stride, got {t.dtype} {tuple(t.shape)}")
+    L.check_device(t)
 
 
 def gemm(
@@ -139,6 +140,7 @@ def im2col_norm(pixels: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
     """uint8 [S,h,w,3] -> bf16 patch matrix [S*(h/p)*(w/p), ld_out] (normalised, zero padded columns)."""
     if pixels.dtype != torch.uint8 or pixels.dim() != 4 or pixels.shape[3] != 3 or not pixels.is_contiguous():
         raise ValueError("im2col_norm: expected contiguous uint8 [S,h,w,3]")
+    L.check_device(pixels)
     S, h, w, _ = pixels.shape
     out = torch.empty((S * (h // patch) * (w // patch), ld_out), dtype=torch.bfloat16, device=pixels.device)
     _launch("im2col", 0.0, L.lib().vr_im2col_norm, pixels.data_ptr(), S, h, w, patch, out.data_ptr(), ld_out, L.stream_ptr())
@@ -148,6 +150,7 @@ def im2col_norm(pixels: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, add: Optional[torch.Tensor] = None):
     """fp32 [M,D] -> bf16 LN(x); with ``add`` [P,D] also returns LN(x)+add[row % P] (bf16)."""
     M, D = x.shape
+    L.check_device(x)
     out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
     out2 = torch.empty_like(out) if add is not None else None
     _launch("norm", 0.0, L.lib().vr_layernorm, x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps, M, D,
@@ -157,6 +160,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
     M, D = x.shape
+    L.check_device(x)
     out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
     _launch("norm", 0.0, L.lib().vr_rmsnorm, x.data_ptr(), x.stride(0), gamma.data_ptr(), eps, M, D, out.data_ptr(),
             out.stride(0), L.stream_ptr())
@@ -165,6 +169,7 @@ def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
 
 def build_lm_input(src: torch.Tensor, embed: torch.Tensor, scale_emb: float, vision: Optional[torch.Tensor]) -> torch.Tensor:
     T, D = src.shape[0], embed.shape[1]
+    L.check_device(embed)
     h = torch.empty((T, D), dtype=torch.float32, device=embed.device)
     _launch("other", 0.0, L.lib().vr_build_lm_input, src.data_ptr(), T, D, embed.data_ptr(), scale_emb, L.ptr(vision),
             0 if vision is None else vision.stride(0), h.data_ptr(), h.stride(0), L.stream_ptr())
@@ -176,6 +181,7 @@ POOLING = {"wmean": 0, "mean": 1, "lasttoken": 2, "cls": 3}
 
 def pool_norm(h: torch.Tensor, gamma: torch.Tensor, eps: float, cu: torch.Tensor, pooling: str, normalize: bool) -> torch.Tensor:
     B = cu.shape[0] - 1
+    L.check_device(h)
     reps = torch.empty((B, h.shape[1]), dtype=torch.float32, device=h.device)
     _launch("other", 0.0, L.lib().vr_pool_norm, h.data_ptr(), h.stride(0), gamma.data_ptr(), eps, cu.data_ptr(), B, h.shape[1],
             POOLING[pooling], int(normalize), reps.data_ptr(), L.stream_ptr())

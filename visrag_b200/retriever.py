@@ -59,13 +59,17 @@ def to_f16_rows(x: torch.Tensor, want_max_norm: bool = False):
 
 
 def build_index(emb, lookup: Optional[List[str]] = None, device: str = "cuda") -> CorpusIndex:
-    """numpy / torch fp32 [nd, d] -> device-resident index."""
+    """numpy / torch fp32 [nd, d] -> device-resident index (a tensor stays on the device it lives on).
+    The tensor-core filter's exactness proof needs finite fp16 copies of Q and D (|x| < 65504). The L2-normalised
+    embeddings of the encoder always are; for anything else the rescoring kernel sees a query or max document row norm
+    that is not < 65504 (inf / NaN included), flags the query, and `score_topk` reruns it through the plain fp32 scan."""
     if isinstance(emb, np.ndarray):
-        emb = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32)).to(device)
+        emb = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32)).to(L.norm_device(device))
     emb = _check_f32(emb, "emb")
     if emb.shape[1] % 8 != 0:
         raise ValueError("embedding dim must be a multiple of 8")
-    f16, mx = to_f16_rows(emb, want_max_norm=True)
+    with L.on_device(emb.device):
+        f16, mx = to_f16_rows(emb, want_max_norm=True)
     return CorpusIndex(emb, f16, mx, lookup)
 
 
@@ -97,6 +101,13 @@ def score_topk(queries: torch.Tensor, index: CorpusIndex, k: int, id_offset: int
     """Exact fp32 top-k of `queries @ index.emb.T`: (scores [nq,k] f32, ids [nq,k] i64 = local index + id_offset).
     Rows are sorted by (score desc, id asc); if k > nd the tail is (-inf, -1)."""
     q = _check_f32(queries, "queries")
+    if q.device != index.emb.device:
+        raise ValueError(f"queries live on {q.device}, the index on {index.emb.device}")
+    with L.on_device(q.device):
+        return _score_topk(q, index, k, id_offset, force_exact, stats)
+
+
+def _score_topk(q: torch.Tensor, index: CorpusIndex, k: int, id_offset: int, force_exact: bool, stats: Optional[dict]):
     nq, d = q.shape
     nd = index.nd
     if nq == 0:
@@ -139,8 +150,9 @@ def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int) -> Tuple[torch.T
     nq, m = scores.shape
     out_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
-    L.check(L.lib().vr_topk_rows(scores.data_ptr(), ids.data_ptr(), nq, m, k, 0, out_s.data_ptr(), out_i.data_ptr(),
-                                 L.stream_ptr()))
+    with L.on_device(scores.device):
+        L.check(L.lib().vr_topk_rows(scores.data_ptr(), ids.data_ptr(), nq, m, k, 0, out_s.data_ptr(), out_i.data_ptr(),
+                                     L.stream_ptr()))
     return out_s, out_i
 
 
