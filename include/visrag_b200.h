@@ -147,9 +147,6 @@ int vr_attention(const vr_attn_params* p, void* stream);
  * 3 = 64-key-block kernel with Q and P in tensor memory, 5 = two-tile kernel with Q in tensor memory as well
  * (both measured slower than the default; kept as tested alternatives) */
 void vr_attention_force_v1(int32_t variant);
-/* debug hook (process-wide): CTA 0 of the persistent attention kernel records its pipeline timeline into `buf`
- * (device memory, [12 warps][cap] uint64 = event << 48 | clock64 low bits; tools/trace_attention.py decodes it); NULL = off */
-void vr_attention_set_trace(void* buf, int32_t cap);
 
 
 /* ------------------------------------------------------------------------------------

@@ -74,8 +74,6 @@ def _declare(lib: C.CDLL) -> None:
     lib.vr_attention.argtypes = [C.POINTER(AttnParams), vp]
     lib.vr_attention_force_v1.restype = None
     lib.vr_attention_force_v1.argtypes = [i32]
-    lib.vr_attention_set_trace.restype = None
-    lib.vr_attention_set_trace.argtypes = [vp, i32]
     lib.vr_im2col_norm.restype = i32
     lib.vr_im2col_norm.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp]
     lib.vr_layernorm.restype = i32

@@ -8,8 +8,7 @@
 namespace vr {
 
 static int g_variant = 0;  // see vr_attention_force_v1()
-static unsigned long long* g_trace = nullptr;  // see vr_attention_set_trace()
-static int g_trace_cap = 0;
+
 
 template <int HS, bool CAUSAL, bool V2>
 static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
@@ -35,8 +34,6 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.ldo = p.ldo;
     a.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
     a.ldq = p.ldq;
-    a.trace = g_trace;
-    a.trace_cap = g_trace_cap;
     if constexpr (V2 && !CAUSAL) {
         if (g_variant == 0) {
             // default for long non-causal sequences (the ViT): persistent decoupled kernel, attention4.cuh
@@ -105,12 +102,6 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
 // where the persistent attention4 kernel is the default, 3 = experimental attention3 kernel,
 // 5 = two-tile kernel with Q in tensor memory too (slower; kept as a measured alternative)
 extern "C" void vr_attention_force_v1(int32_t variant) { vr::g_variant = variant; }
-
-// debug hook: CTA 0 of the persistent kernel records (event, clock64) pairs per warp into `buf` ([12][cap] uint64; NULL = off)
-extern "C" void vr_attention_set_trace(void* buf, int32_t cap) {
-    vr::g_trace = reinterpret_cast<unsigned long long*>(buf);
-    vr::g_trace_cap = buf ? cap : 0;
-}
 
 extern "C" int vr_attention(const vr_attn_params* p, void* stream) {
     using namespace vr;

@@ -54,8 +54,6 @@ struct AttArgs {
     long long ldo;
     const __nv_bfloat16* q;  // query matrix base (kernels that stage Q themselves instead of through TMA)
     long long ldq;
-    unsigned long long* trace;  // debug timeline (attention4 only): [12 warps][trace_cap] of (event << 48 | clock & (2^48-1)); CTA 0 writes
-    int trace_cap;
 };
 
 struct AttMaps {
