@@ -261,7 +261,11 @@ def run_ours(a):
             kk = "gemm" if k.startswith("gemm:") else k
             shares[kk] = round(shares.get(kk, 0.0) + v[1] / all_ms, 4)
 
-    # ---- (4) queries: encode text queries + exact top-10 over a page-sharded corpus
+    # ---- (4) queries: encode text queries + exact top-10 over a page-sharded corpus.
+    # Corpus sharded by page (rank r holds pages shard_range(nd*world, r, world)); the query ENCODE is sharded by rank as in
+    # the reference (dense_retriever.py:48-50): rank r encodes queries shard_range(nq, r, world), ONE all-gather of the
+    # [nq/world, 2304] fp32 embeddings makes them global, every rank scores all queries against its shard, ONE all-gather
+    # of [nq, 10] (score, id) pairs + a k-way merge finishes (retriever.gather_queries / sharded_topk).
     nq, nd = a.queries, a.corpus
     from visrag_b200.synth import synth_queries
     qtexts = synth_queries(nq, 7)
@@ -270,24 +274,28 @@ def run_ours(a):
     corpus = torch.nn.functional.normalize(torch.randn(hi - lo, cfg.hidden, device=dev, generator=g), dim=1)
     index = retriever.build_index(corpus)
     qb = a.query_batch
+    qlo, qhi = retriever.shard_range(nq, rank, world)
+    my_q = qtexts[qlo:qhi]
+
+    def encode_my_queries():
+        outs = [eng.encode(my_q[i:i + qb], [None] * len(my_q[i:i + qb]), tok) for i in range(0, len(my_q), qb)]
+        local = torch.cat(outs) if outs else torch.zeros((0, cfg.hidden), dtype=torch.float32, device=dev)
+        return retriever.gather_queries(local, nq)
 
     def queries_step():
-        outs = []
-        for i in range(0, nq, qb):
-            outs.append(eng.encode(qtexts[i:i + qb], [None] * len(qtexts[i:i + qb]), tok))
-        qe = torch.cat(outs)
+        qe = encode_my_queries()
         s, ids = retriever.sharded_topk(qe, index, 10, lo)
-        return s.cpu(), ids.cpu()
+        return s.cpu(), ids.cpu(), qe
 
     queries_step()
     barrier()
     e0.record()
     for _ in range(a.query_reps):
-        s_top, i_top = queries_step()
+        s_top, i_top, qe_all = queries_step()
     e1.record()
     barrier()
     q_ms = max_over_ranks(e0.elapsed_time(e1)) / a.query_reps
-    qe = torch.nn.functional.normalize(torch.randn(nq, cfg.hidden, device=dev, generator=g), dim=1)
+    qe = torch.nn.functional.normalize(torch.randn(nq, cfg.hidden, device=dev, generator=torch.Generator(device=dev).manual_seed(77)), dim=1)
     retriever.sharded_topk(qe, index, 10, lo)
     barrier()
     e0.record()
@@ -296,6 +304,110 @@ def run_ours(a):
     e1.record()
     barrier()
     r_ms = max_over_ranks(e0.elapsed_time(e1)) / a.query_reps
+
+    def check_against_torch(q_all, idx, lo_, k=10, n_check=64):
+        """Correctness under NCCL, outside every timed region: the sharded result of `n_check` queries vs an independent
+        route - torch.matmul + torch.topk on every rank's fp32 shard, all_gather of those partial lists, torch.topk merge.
+        Raises on any id mismatch (scores within 2e-6)."""
+        sub = q_all[:n_check].contiguous()
+        got_s, got_i = retriever.sharded_topk(sub, idx, k, lo_)
+        ref = torch.topk(sub @ idx.emb.T, k, dim=1)
+        ref_s, ref_i = ref.values.contiguous(), (ref.indices + lo_).contiguous()
+        if world > 1:
+            all_s = [torch.empty_like(ref_s) for _ in range(world)]
+            all_i = [torch.empty_like(ref_i) for _ in range(world)]
+            dist.all_gather(all_s, ref_s)
+            dist.all_gather(all_i, ref_i)
+            cs, ci = torch.cat(all_s, dim=1), torch.cat(all_i, dim=1)
+            top = torch.topk(cs, k, dim=1)
+            ref_s, ref_i = top.values, torch.gather(ci, 1, top.indices)
+        ok = bool(torch.equal(got_i, ref_i)) and float((got_s - ref_s).abs().max()) <= 2e-6
+        if not ok:
+            raise SystemExit(f"rank {rank}: sharded_topk disagrees with the torch fp32 route under world={world}")
+        return n_check
+
+    checked = check_against_torch(qe, index, lo)
+    # every rank must hold the same global query embeddings after gather_queries (bitwise)
+    if world > 1:
+        ref_q = qe_all.clone()
+        dist.broadcast(ref_q, 0)
+        if not torch.equal(ref_q, qe_all):
+            raise SystemExit(f"rank {rank}: gathered query embeddings differ from rank 0's")
+
+    # ---- (4b) BASELINE configs[3] retrieval at its stated size: `--big-corpus` pages per GPU (125 000 x 8 = 1 M) resident as
+    # fp32 + fp16, `--big-queries` queries, top-10, staged timing (filter / rescore / all-gather / merge)
+    big = None
+    if a.big_corpus > 0:
+        del index, corpus
+        torch.cuda.empty_cache()
+        blo, bhi = retriever.shard_range(a.big_corpus * world, rank, world)
+        gen = torch.Generator(device=dev).manual_seed(900 + rank)
+        bc = torch.empty((bhi - blo, cfg.hidden), dtype=torch.float32, device=dev)
+        for r0 in range(0, bhi - blo, 32768):
+            x = torch.randn((min(32768, bhi - blo - r0), cfg.hidden), device=dev, generator=gen)
+            bc[r0:r0 + x.shape[0]] = torch.nn.functional.normalize(x, dim=1)
+        barrier()
+        e0.record()
+        bindex = retriever.build_index(bc)
+        e1.record()
+        barrier()
+        build_ms = max_over_ranks(e0.elapsed_time(e1))
+        bq = torch.nn.functional.normalize(torch.randn(a.big_queries, cfg.hidden, device=dev,
+                                                       generator=torch.Generator(device=dev).manual_seed(901)), dim=1)
+        st = {}
+        retriever.sharded_topk(bq, bindex, 10, blo, stats=st)
+        barrier()
+        st = {"stages": {}}
+        e0.record()
+        for _ in range(a.query_reps):
+            retriever.sharded_topk(bq, bindex, 10, blo, stats=st)
+        e1.record()
+        barrier()
+        big_ms = max_over_ranks(e0.elapsed_time(e1)) / a.query_reps
+        stages = {k: round(v / a.query_reps, 3) for k, v in retriever.resolve_stages(st).items()}
+        filt_tf = 2.0 * a.big_queries * (bhi - blo) * cfg.hidden / (stages.get("filter", float("inf")) / 1e3) / 1e12
+        checked_big = check_against_torch(bq, bindex, blo)
+        big = {"workload": "BASELINE configs[3]: synthetic unit-norm corpus sharded by page, index build (fp32 -> fp16 copy + row norms) + "
+                           "top-10 of every query over the FULL corpus with the partial-top-k all-gather",
+               "corpus_pages": a.big_corpus * world, "pages_per_gpu": bhi - blo, "queries": a.big_queries, "k": 10,
+               "index_build_ms": round(build_ms, 2), "ms_per_query_batch": round(big_ms, 3),
+               "queries_per_s": round(a.big_queries / (big_ms / 1e3), 1), "stages_ms_rank0": stages,
+               "filter_tflops_fp16_per_gpu": round(filt_tf, 1), "filter_frac_of_tensor_peak": round(filt_tf / peak_tf, 3),
+               "flagged": st.get("flagged"), "checked_queries_vs_torch_fp32": checked_big}
+
+    # ---- (4c) the reference's own operating point (eval.sh: per-device batch 16) and the demo's single query, blocking API
+    small = None
+    if a.small_batch > 0 and P >= a.small_batch:
+        sb_items = {k: v[: a.small_batch] for k, v in items.items()}
+        for _ in range(3):
+            model(passage=sb_items, tokenizer=tok, max_inp_length=2048).p_reps.cpu()
+        barrier()
+        e0.record()
+        for _ in range(10):
+            model(passage=sb_items, tokenizer=tok, max_inp_length=2048).p_reps.cpu()
+        e1.record()
+        barrier()
+        sb_ms = max_over_ranks(e0.elapsed_time(e1)) / 10
+        q1 = {"id": ["q"], "text": [qtexts[0]], "image": [None]}
+        idx1 = retriever.build_index(torch.nn.functional.normalize(
+            torch.randn(nd, cfg.hidden, device=dev, generator=torch.Generator(device=dev).manual_seed(3)), dim=1))
+
+        def one_query():
+            qv = model(query=q1, tokenizer=tok, max_inp_length=2048).q_reps
+            return retriever.score_topk(qv, idx1, 10)[1].cpu()
+
+        for _ in range(3):
+            one_query()
+        barrier()
+        t_q = time.perf_counter()
+        for _ in range(20):
+            one_query()
+        torch.cuda.synchronize()
+        q_lat_ms = (time.perf_counter() - t_q) / 20 * 1e3
+        small = {"pages_per_s_batch": a.small_batch, "pages_per_s": round(world * a.small_batch / (sb_ms / 1e3), 1),
+                 "ms_per_batch": round(sb_ms, 2), "api": "DRModelForInference.forward(passage=...).p_reps.cpu(), host PIL pages in",
+                 "single_query_encode_plus_top10_ms": round(q_lat_ms, 2), "single_query_corpus_pages": nd}
+        del idx1
 
     # ---- (5) CPU baseline: the oracle port of the reference algorithm on the host cores (rank 0, N = 1 only)
     cpu_baseline = None
@@ -315,13 +427,19 @@ def run_ours(a):
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / a.steps, 3), "batch_intervals_ms": intervals,
                     "api": "inference.encode_stream (loop body of distributed_parallel_embedding_inference) over DRModelForInference",
+                    "inputs": "the same 128 host PIL pages every step: nothing in the prep path caches per image (only the placeholder "
+                              "string is memoised), but Pillow's zero-copy row export always finds the pages warm in the host caches",
                     "blocking": {"value": round(blocking_value, 2), "ms_per_step": round(blocking_ms / a.steps, 3),
                                  "api": "DRModelForInference.forward(passage=..., tokenizer=...).p_reps.cpu() per step"}},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "kernel_time_share": shares,
             "model_tflops": round(total_flops_per_page(n_patches, lm_tokens) * value / 1e12 / world, 1) if n_patches else None,
             "queries": {"queries_per_s_encode_plus_top10": round(nq / (q_ms / 1e3), 1), "retrieve_only_queries_per_s": round(nq / (r_ms / 1e3), 1),
-                        "n_queries": nq, "corpus_pages": nd * world, "k": 10, "collective": "1 all_gather of [nq,10] (score,id)" if world > 1 else None},
+                        "n_queries": nq, "corpus_pages": nd * world, "k": 10, "query_encode": f"sharded by rank ({qhi - qlo} of {nq} on rank 0)",
+                        "collectives": (["all_gather_into_tensor of [ceil(nq/world), 2304] fp32 query embeddings",
+                                         "all_gather_into_tensor of [nq, 10] (score, id) pairs"] if world > 1 else []),
+                        "checked_vs_torch_fp32_under_nccl": checked},
+            "retrieval_configs3": big, "small_batch": small,
             "cpu_baseline": cpu_baseline, "setup_s": round(setup_s, 1),
         }
         print(json.dumps(line), flush=True)
@@ -435,6 +553,10 @@ def main():
     ap.add_argument("--page-px", type=int, default=448)
     ap.add_argument("--queries", type=int, default=1000)
     ap.add_argument("--corpus", type=int, default=10000, help="corpus pages per GPU for the retrieval figure")
+    ap.add_argument("--big-corpus", type=int, default=-1,
+                    help="pages per GPU of the configs[3] retrieval leg (default: 125000 when N > 1, off at N = 1; 0 = off)")
+    ap.add_argument("--big-queries", type=int, default=10000)
+    ap.add_argument("--small-batch", type=int, default=16, help="pages per call of the small-batch figure (0 = off)")
     ap.add_argument("--query-batch", type=int, default=500)
     ap.add_argument("--query-reps", type=int, default=3)
     ap.add_argument("--cpu-pages", type=int, default=2)
@@ -442,6 +564,8 @@ def main():
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":
         a.warmup = 3
+    if a.big_corpus < 0:
+        a.big_corpus = 125000 if a.gpus > 1 else 0
     if a.impl == "reference":
         run_reference(a)
     else:

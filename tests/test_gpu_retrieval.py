@@ -155,3 +155,101 @@ def test_knowledge_base_single_query_retrieval(tmp_path):
     KB.save_knowledge_base(str(tmp_path / "s"), D[:3], names[:3])
     small.__init__(str(tmp_path / "s"))
     assert len(small.retrieve(D[:1], 10)) == 3
+
+
+from visrag_b200 import retriever as R  # noqa: E402  (importing does not load the CUDA library)
+
+
+def _nccl_worker(rank, world, port, out_q):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        dev = f"cuda:{rank}"
+        g = torch.Generator(device=dev).manual_seed(1234)           # same stream on every rank: the FULL corpus / query set
+        D = torch.nn.functional.normalize(torch.randn(6000, 256, device=dev, generator=g), dim=1)
+        Q = torch.nn.functional.normalize(torch.randn(1000, 256, device=dev, generator=g), dim=1)
+        lo, hi = R.shard_range(D.shape[0], rank, world)
+        index = R.build_index(D[lo:hi].contiguous())
+        # queries sharded for "encoding" (here: each rank simply owns a slice), gathered, then the partial-top-k exchange
+        qlo, qhi = R.shard_range(Q.shape[0], rank, world)
+        q_all = R.gather_queries(Q[qlo:qhi].contiguous(), Q.shape[0])
+        ok = bool(torch.equal(q_all, Q))
+        stats = {}
+        s, i = R.sharded_topk(q_all, index, 10, lo, stats=stats)
+        ref = torch.topk(Q @ D.T, 10, dim=1)                         # brute-force fp32 scan of the whole corpus
+        ok = ok and bool(torch.equal(i, ref.indices)) and float((s - ref.values).abs().max()) <= 2e-6
+        out_q.put((rank, ok, stats.get("path")))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_topk_under_nccl_equals_the_brute_force_scan():
+    """World-size-2 NCCL run on two real GPUs (skipped on a one-GPU box): query all-gather + partial-top-k all-gather +
+    merge kernel give exactly the ids of a brute-force fp32 scan of the unsharded corpus, on every rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] for r in res), res
+    assert all(r[2] == "filter+rescore" for r in res)
+
+
+def test_engine_and_index_on_a_non_current_device():
+    """kernels must launch on the device that owns the buffers, not on the process's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tests.helpers import cosine_rows, synth_pages
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.encoder import VisRAGEngine
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    torch.cuda.set_device(0)
+    cfg = VisRAGConfig.tiny()
+    sd = random_state_dict(cfg, 11)
+    tok = StubTokenizer(cfg.vocab)
+    pages = synth_pages([(448, 448), (700, 900)], 4)
+    e0, e1 = VisRAGEngine(cfg, sd, "cuda:0"), VisRAGEngine(cfg, sd, "cuda:1")
+    a = e0.encode(["", ""], pages, tok)
+    b = e1.encode(["", ""], pages, tok)          # cuda:0 is still the current device
+    assert b.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(a.cpu(), b.cpu())
+    rs = np.random.RandomState(0)
+    D = rs.randn(9000, 256).astype(np.float32)
+    Q = rs.randn(600, 256).astype(np.float32)
+    i0 = R.score_topk(torch.from_numpy(Q).to("cuda:0"), R.build_index(D, device="cuda:0"), 10)[1]
+    i1 = R.score_topk(torch.from_numpy(Q).to("cuda:1"), R.build_index(D, device="cuda:1"), 10)[1]
+    assert torch.equal(i0.cpu(), i1.cpu())
+
+
+def test_non_finite_and_out_of_fp16_range_inputs_fall_back_to_the_fp32_scan():
+    """|x| > 65504 or NaN would become inf/NaN in the fp16 copies; the rescoring kernel flags those queries (or
+    every query when the corpus is affected) and the fp32 scan answers them."""
+    rs = np.random.RandomState(3)
+    D = rs.randn(8000, 256).astype(np.float32)
+    Q = rs.randn(700, 256).astype(np.float32)
+    Q[5] *= 1e6                                  # fp16 overflow in one query
+    Dbig = D.copy()
+    Dbig[17] *= 1e6                              # fp16 overflow in one document: the whole index is affected
+    for dd in (D, Dbig):
+        stats = {}
+        s, i = R.score_topk(torch.from_numpy(Q).cuda(), R.build_index(dd), 10, stats=stats)
+        ref = torch.topk(torch.from_numpy(Q).cuda().double() @ torch.from_numpy(dd).cuda().double().T, 10, dim=1)
+        assert torch.equal(i, ref.indices), stats
+        assert stats["flagged"] >= 1

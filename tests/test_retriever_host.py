@@ -50,6 +50,11 @@ def _worker(rank, world, port, q_out):
     gs, gi = R.gather_partials(torch.from_numpy(s), torch.from_numpy(i + lo))
     ms, mi = O.merge_topk([(gs.numpy(), gi.numpy())], 4)
     want_s, want_i = O.score_topk(Q, D, 4)
+    # query encode sharded by rank: each rank holds its slice of the query embeddings, one all-gather restores the order
+    for nq in (6, 5, 1):
+        qlo, qhi = R.shard_range(nq, rank, world)
+        allq = R.gather_queries(torch.from_numpy(Q[:nq][qlo:qhi].copy()), nq)
+        assert np.array_equal(allq.numpy(), Q[:nq]), (nq, rank)
     q_out.put((rank, bool(np.array_equal(mi, want_i) and np.allclose(ms, want_s)), tuple(gs.shape)))
     dist.destroy_process_group()
 

@@ -107,6 +107,32 @@ def score_topk(queries: torch.Tensor, index: CorpusIndex, k: int, id_offset: int
         return _score_topk(q, index, k, id_offset, force_exact, stats)
 
 
+class _Stages:
+    """Optional per-stage CUDA-event timing: pass stats={"stages": {}} and read stats["stages"] (ms) after a synchronize."""
+
+    def __init__(self, stats: Optional[dict]):
+        self.on = stats is not None and "stages" in stats
+        self.stats = stats
+        if self.on:
+            self.last = torch.cuda.Event(enable_timing=True)
+            self.last.record()
+            stats.setdefault("_events", [])
+
+    def mark(self, name: str) -> None:
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.stats["_events"].append((name, self.last, e))
+            self.last = e
+
+
+def resolve_stages(stats: dict) -> dict:
+    """After torch.cuda.synchronize(): turn the recorded event pairs into stats["stages"][name] += ms."""
+    for name, e0, e1 in stats.pop("_events", []):
+        stats["stages"][name] = stats["stages"].get(name, 0.0) + e0.elapsed_time(e1)
+    return stats["stages"]
+
+
 def _score_topk(q: torch.Tensor, index: CorpusIndex, k: int, id_offset: int, force_exact: bool, stats: Optional[dict]):
     nq, d = q.shape
     nd = index.nd
@@ -128,11 +154,15 @@ def _score_topk(q: torch.Tensor, index: CorpusIndex, k: int, id_offset: int, for
     out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     flags = torch.empty((nq,), dtype=torch.int32, device=q.device)
     sp = L.stream_ptr()
+    ev = _Stages(stats)
+    ev.mark("q_to_f16")
     L.check(lib.vr_score_filter(q16.data_ptr(), nq, index.emb_f16.data_ptr(), nd, d, ranges, cand_s.data_ptr(),
                                 cand_i.data_ptr(), sp))
+    ev.mark("filter")
     L.check(lib.vr_score_rescore(q.data_ptr(), nq, index.emb.data_ptr(), nd, d, ranges, cand_s.data_ptr(), cand_i.data_ptr(),
                                  index.max_norm.data_ptr(), k, id_offset, out_s.data_ptr(), out_i.data_ptr(),
                                  flags.data_ptr(), sp))
+    ev.mark("rescore")
     bad = torch.nonzero(flags).flatten()  # host sync: the caller reads the result next anyway
     if stats is not None:
         stats.update(path="filter+rescore", flagged=int(bad.numel()), ranges=ranges)
@@ -180,16 +210,42 @@ def gather_partials(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tupl
     return gs.contiguous(), gi.contiguous()
 
 
-def sharded_topk(queries: torch.Tensor, index: CorpusIndex, k: int, id_offset: int, group=None):
+def sharded_topk(queries: torch.Tensor, index: CorpusIndex, k: int, id_offset: int, group=None, stats: Optional[dict] = None):
     """Corpus sharded by page across ranks (every rank holds the same queries): local exact top-k with GLOBAL ids,
     one all-gather of [nq, k] (score, id) pairs over NCCL/NVLink, k-way merge on every rank."""
     import torch.distributed as dist
 
-    s, i = score_topk(queries, index, k, id_offset)
+    s, i = score_topk(queries, index, k, id_offset, stats=stats)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return s, i
+    ev = _Stages(stats)
     gs, gi = gather_partials(s, i, group)
-    return merge_topk(gs, gi, k)
+    ev.mark("all_gather_partials")
+    out = merge_topk(gs, gi, k)
+    ev.mark("merge")
+    return out
+
+
+def gather_queries(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Queries sharded by rank for ENCODING (the reference's partition, `dense_retriever.py:48-50`): rank r encoded
+    queries shard_range(n_total, r, world); one all-gather of the [ceil(n/world), d] fp32 blocks gives every rank all
+    n_total embeddings in query order (10 k x 2304 fp32 = 92 MB: sub-millisecond over NVLink)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    d = local.shape[1]
+    block = torch.zeros((per, d), dtype=local.dtype, device=local.device)
+    block[: local.shape[0]] = local
+    flat = torch.empty((world * per, d), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(flat, block, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(flat[r * per: r * per + (hi - lo)])
+    return torch.cat(parts)
 
 
 # ------------------------------------------------------------------------------------------------------
