@@ -299,3 +299,53 @@ def test_mixed_resolution_corpus_recall_parity():
     full = q_ref @ p_ref.T
     for qi in range(len(queries)):
         assert (full[qi, i_run[qi]] >= s_ref[qi, -1] - 2e-3).all()
+
+
+def test_build_from_checkpoint_directory(tmp_path):
+    """`DRModelForInference.build(model_args)` - what the reference driver's `setup_model` calls (`driver/eval.py:118-134`) - on
+    a synthetic HF checkpoint directory in the public checkpoint's layout (config.json + sharded *.safetensors, bf16): the
+    loaded model gives bit-identical embeddings to an engine built from the same state dict in memory and matches the
+    oracle; `.to()` / `.eval()` return the model; the pickle shards it writes load with the reference's format reader.
+    (The reference-side half - the unmodified driver driving these classes - is tests/test_dropin_reference_driver.py.)"""
+    from types import SimpleNamespace
+
+    from oracle import restated as O
+    from visrag_b200 import inference as I
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.modeling import DRModelForInference
+    from visrag_b200.synth import synth_doc_pages
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict, save_checkpoint
+
+    cfg = VisRAGConfig.tiny()
+    sd = random_state_dict(cfg, 77)
+    ckpt = str(tmp_path / "VisRAG-Ret-synthetic")
+    save_checkpoint(ckpt, cfg, sd)
+    margs = SimpleNamespace(model_name_or_path=ckpt, pooling="wmean", normalize=True, cache_dir=None)
+    model = DRModelForInference.build(model_args=margs, cache_dir=None)
+    assert model.to("cuda:0") is model and model.eval() is model and model.pooling == "wmean" and model.lm_q.config == cfg
+    tok = StubTokenizer(cfg.vocab)
+    pages = synth_doc_pages([(448, 448), (700, 900), (640, 300)], 31)
+    batch = _items([""] * 3, pages, "d")
+    got = model(passage=batch, tokenizer=tok, max_inp_length=2048).p_reps
+    direct = _engine_model(cfg, sd)(passage=batch, tokenizer=tok, max_inp_length=2048).p_reps
+    assert torch.equal(got, direct)
+    assert cosine_rows(got.cpu().numpy(), O.encode(sd, cfg, tok, [""] * 3, pages)).min() >= COS_MIN
+    args = SimpleNamespace(output_dir=str(tmp_path / "out"), per_device_eval_batch_size=2, max_inmem_docs=100, world_size=1,
+                           process_index=0, device="cuda:0")
+    I.distributed_parallel_embedding_inference([{"id": f"d{i}", "text": "", "image": im} for i, im in enumerate(pages)], model, args,
+                                               "corpus", True, {"tokenizer": tok, "max_inp_length": 2048})
+    import pickle
+
+    with open(str(tmp_path / "out" / "embeddings.corpus.rank.0.0-3"), "rb") as f:
+        emb, ids = pickle.load(f)                      # `dense_retriever.py:19-23`
+    assert ids == ["d0", "d1", "d2"] and emb.dtype == np.float32 and np.array_equal(emb, got.cpu().numpy())
+    # a config the packing code does not implement must be refused, not silently mis-tokenised
+    import json
+
+    bad = json.load(open(ckpt + "/config.json"))
+    bad["slice_mode"] = False
+    from visrag_b200.modeling import config_from_hf
+
+    with pytest.raises(NotImplementedError):
+        config_from_hf(bad)

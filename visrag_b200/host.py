@@ -15,6 +15,10 @@ import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import threading
+import weakref
+from collections import OrderedDict
+
 import numpy as np
 
 from .config import VisRAGConfig
@@ -109,20 +113,43 @@ def placeholder_text(plan: Optional[SlicePlan], tokenizer, query_num: int) -> st
     return text
 
 
-_TOK_CACHE: Dict[Tuple[int, str, Optional[int]], Tuple[np.ndarray, np.ndarray]] = {}
+_TOK_CACHE_MAX = 4096
+_TOK_CACHES = weakref.WeakKeyDictionary()  # tokenizer object -> OrderedDict (LRU); dies with the tokenizer
+_TOK_CACHES_LOCK = threading.Lock()
+
+
+def _tok_cache(tokenizer):
+    """The memo lives and dies with the tokenizer OBJECT (weak reference): `id()` values are reused after garbage
+    collection, so a cache keyed on them could hand a new tokenizer another vocabulary's ids. Tokenizers that cannot be
+    weakly referenced get no cache."""
+    try:
+        with _TOK_CACHES_LOCK:
+            c = _TOK_CACHES.get(tokenizer)
+            if c is None:
+                c = _TOK_CACHES[tokenizer] = OrderedDict()
+            return c
+    except TypeError:
+        return None
 
 
 def tokenize(content: str, tokenizer, max_inp_length: Optional[int]) -> Tuple[np.ndarray, np.ndarray]:
     """ids (int32) truncated to max_inp_length and image_bound [n,2] = (index after <image>, index of </image>).
-    Pure function of (tokenizer, content, max length): results are memoised (every single-slice page shares one
-    placeholder string, so a corpus batch tokenises it once)."""
-    key = (id(tokenizer), content, max_inp_length)
-    hit = _TOK_CACHE.get(key)
-    if hit is not None:
-        return hit
+    Pure function of (tokenizer, content, max length): results are memoised per tokenizer object, LRU (every single-slice
+    page shares one placeholder string, so a corpus batch tokenises it once)."""
+    cache = _tok_cache(tokenizer)
+    key = (content, max_inp_length)
+    if cache is not None:
+        with _TOK_CACHES_LOCK:
+            hit = cache.get(key)
+            if hit is not None:
+                cache.move_to_end(key)
+                return hit
     out = _tokenize(content, tokenizer, max_inp_length)
-    if len(_TOK_CACHE) < 4096:
-        _TOK_CACHE[key] = out
+    if cache is not None:
+        with _TOK_CACHES_LOCK:
+            cache[key] = out
+            if len(cache) > _TOK_CACHE_MAX:
+                cache.popitem(last=False)
     return out
 
 

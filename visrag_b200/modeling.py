@@ -42,9 +42,26 @@ class DROutput:
     accuracy: torch.Tensor = None
 
 
+_VISION_ENCODERS = {  # timm model name -> (dim, blocks defined, heads, mlp); `vision_transformer.py:2612-2619`
+    "vit_so400m_patch14_siglip_384": (1152, 27, 16, 4304),
+}
+
+
 def config_from_hf(d: dict) -> VisRAGConfig:
-    """MiniCPM-V `config.json` -> VisRAGConfig (field names `configuration_minicpm.py:109-160,197-222`)."""
+    """MiniCPM-V `config.json` -> VisRAGConfig (field names `configuration_minicpm.py:109-160,197-222`). The vision tower is
+    named by `vision_encoder` (+ `drop_vision_last_layer`, `modeling_minicpmv.py:57-73`) in real checkpoints; synthetic ones
+    written by `weights.save_checkpoint` carry explicit `vit_*` fields (reduced towers have no timm name)."""
     base = VisRAGConfig()
+    if not d.get("slice_mode", True):
+        # `prepare_context` emits ONE un-sliced image and a single placeholder when slice_mode is off
+        # (`modeling_visrag_ret.py:57-84`); the packing code here always slices, so refuse rather than embed other tokens
+        raise NotImplementedError("config.json has slice_mode=false: the un-sliced path of VisRAG_Ret.prepare_context is not implemented")
+    if "vit_dim" not in d and d.get("vision_encoder") is not None:
+        enc = d["vision_encoder"]
+        if enc not in _VISION_ENCODERS:
+            raise NotImplementedError(f"vision_encoder {enc!r}: only {sorted(_VISION_ENCODERS)} is supported")
+        dim, depth, heads, mlp = _VISION_ENCODERS[enc]
+        d = dict(d, vit_dim=dim, vit_depth=depth - (1 if d.get("drop_vision_last_layer", True) else 0), vit_heads=heads, vit_mlp=mlp)
     return VisRAGConfig(
         patch_size=d.get("patch_size", base.patch_size), query_num=d.get("query_num", base.query_num),
         hidden=d.get("hidden_size", base.hidden), layers=d.get("num_hidden_layers", base.layers),
@@ -106,6 +123,9 @@ class VisRAGRetB200:
                                       "(`modeling_visrag_ret.py:106-111`)")
         eng = self.engine
         pb = prepare_batch(text, image, tokenizer, self.config, max_inp_length, eng.device_frontend)
+        if pb.n_items and int(pb.seq_lens.max()) > self.config.max_pos:
+            raise ValueError(f"sequence of {int(pb.seq_lens.max())} tokens exceeds max_position_embeddings={self.config.max_pos} "
+                             "(the RoPE tables end there); lower max_inp_length")
         groups, src, pos, cu = eng.upload(pb)
         vision = eng.encode_vision(groups, pb.group_row0, pb.n_slices)
         h = eng.lm_hidden(src, pos, cu, int(pb.seq_lens.max()), vision)

@@ -132,3 +132,43 @@ def random_state_dict_device(cfg: VisRAGConfig, seed: int, device: str) -> Dict[
             t = 0.02 * torch.randn(shape, generator=g, device=device)
         out[name] = t.to(torch.bfloat16)
     return out
+
+
+def hf_config_dict(cfg: VisRAGConfig, name: str = "VisRAG-Ret-synthetic") -> dict:
+    """`config.json` of a checkpoint directory (MiniCPM-V field names, `configuration_minicpm.py:109-160,197-222`);
+    `_name_or_path` is what the reference driver dispatches the tokenizer class on (`driver/eval.py:102-110,306-316`)."""
+    d = {
+        "_name_or_path": name, "architectures": ["VisRAG_Ret"], "model_type": "minicpmv",
+        "hidden_size": cfg.hidden, "num_hidden_layers": cfg.layers, "num_attention_heads": cfg.heads,
+        "num_key_value_heads": cfg.heads, "intermediate_size": cfg.inter, "vocab_size": cfg.vocab, "scale_emb": cfg.scale_emb,
+        "scale_depth": cfg.scale_depth, "dim_model_base": 256, "rms_norm_eps": cfg.rms_eps, "rope_theta": cfg.rope_theta,
+        "max_position_embeddings": cfg.max_pos, "hidden_act": "silu", "query_num": cfg.query_num, "patch_size": cfg.patch_size,
+        "scale_resolution": cfg.scale_resolution, "max_slice_nums": cfg.max_slice_nums, "slice_mode": cfg.slice_mode,
+        "drop_vision_last_layer": True, "torch_dtype": "bfloat16",
+    }
+    if (cfg.vit_dim, cfg.vit_depth, cfg.vit_heads, cfg.vit_mlp) == (1152, 26, 16, 4304):
+        d["vision_encoder"] = "vit_so400m_patch14_siglip_384"
+    else:  # reduced test towers have no timm name
+        d.update(vit_dim=cfg.vit_dim, vit_depth=cfg.vit_depth, vit_heads=cfg.vit_heads, vit_mlp=cfg.vit_mlp)
+    return d
+
+
+def save_checkpoint(path: str, cfg: VisRAGConfig, state_dict: Dict[str, torch.Tensor], name: str = "VisRAG-Ret-synthetic",
+                    shards: int = 2) -> None:
+    """Write a HF-style checkpoint directory (`config.json` + `model-0000i-of-0000n.safetensors`, bf16) that
+    `DRModelForInference.build` / `VisRAGRetB200.from_pretrained` load - the layout of the public VisRAG-Ret checkpoint.
+    Used to exercise the loading path without network access to the real weights."""
+    import json
+    import os
+
+    from safetensors.torch import save_file
+
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(hf_config_dict(cfg, name), f, indent=1)
+    names = list(state_dict)
+    per = (len(names) + shards - 1) // shards
+    for i in range(shards):
+        part = {k: state_dict[k].detach().to("cpu", torch.bfloat16).contiguous() for k in names[i * per:(i + 1) * per]}
+        if part:
+            save_file(part, os.path.join(path, f"model-{i + 1:05d}-of-{shards:05d}.safetensors"))
