@@ -253,3 +253,38 @@ def test_non_finite_and_out_of_fp16_range_inputs_fall_back_to_the_fp32_scan():
         ref = torch.topk(torch.from_numpy(Q).cuda().double() @ torch.from_numpy(dd).cuda().double().T, 10, dim=1)
         assert torch.equal(i, ref.indices), stats
         assert stats["flagged"] >= 1
+
+
+@pytest.mark.parametrize("nq,nd,d", [(700, 33333, 256), (257, 70001, 128), (2600, 9000, 64), (100, 50000, 2304)])
+def test_filter_candidate_lists_cover_every_query_block_piece(nq, nd, d):
+    """The filter's work split (contiguous spans of 256x256 tiles per CTA pair) must leave every list slot of every
+    query written: a real sorted list or an empty one. Buffers are poisoned first; then the union of a query's lists has
+    to contain the fp16-approximate top-16 of the whole corpus (every list keeps the best 16 of its span)."""
+    from visrag_b200 import _lib as L
+    from visrag_b200 import retriever as R
+
+    rs = np.random.RandomState(nq)
+    Q, D = _unit(rs, nq, d), _unit(rs, nd, d)
+    q = torch.from_numpy(Q).cuda()
+    idx = R.build_index(D)
+    lib = L.lib()
+    ranges = lib.vr_score_ranges(nq, nd)
+    kt = lib.vr_score_list_len()
+    lists = ranges * 2
+    cand_s = torch.full((nq, lists * kt), float("nan"), device="cuda")
+    cand_i = torch.full((nq, lists * kt), 0x7F7F7F7F, dtype=torch.int32, device="cuda")
+    q16 = R.to_f16_rows(q)
+    L.check(lib.vr_score_filter(q16.data_ptr(), nq, idx.emb_f16.data_ptr(), nd, d, ranges, cand_s.data_ptr(), cand_i.data_ptr(),
+                                L.stream_ptr()))
+    torch.cuda.synchronize()
+    ci, cs = cand_i.cpu().numpy().reshape(nq, lists, kt), cand_s.cpu().numpy().reshape(nq, lists, kt)
+    assert not np.isnan(cs).any() and ((ci == -1) | ((ci >= 0) & (ci < nd))).all()
+    assert (np.diff(cs, axis=2) <= 0).all()                       # every list sorted descending (empties are -inf)
+    assert (np.isinf(cs) == (ci == -1)).all()
+    approx = (q16.float() @ idx.emb_f16.float().T).cpu().numpy()  # fp16 operands, fp32 accumulate like the filter
+    for r in rs.choice(nq, 40, replace=False):
+        have = set(ci[r][ci[r] >= 0].tolist())
+        assert len(have) == (ci[r] >= 0).sum()                    # no doc in two lists
+        kth = np.sort(approx[r])[-kt]
+        must = set(np.nonzero(approx[r] > kth + 1e-4)[0].tolist())  # clear members of the approximate top-16
+        assert must <= have

@@ -28,13 +28,20 @@ def stage_elementwise():
     torch.manual_seed(0)
     ok = True
     dev = "cuda"
-    px = torch.randint(0, 256, (3, 28, 42, 3), dtype=torch.uint8, device=dev)
-    got = ops.im2col_norm(px, 14, 640)
-    # reference arithmetic on the CPU like torchvision's ToTensor/Normalize (true division; CUDA torch divides by reciprocal)
-    x = ((px.cpu().float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2)  # [S,3,h,w]
-    want = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588).to(dev)
-    ok &= report("im2col", got[:, :588], want.bfloat16(), 1e-6)
-    ok &= report("im2col pad", got[:, 588:], torch.zeros_like(got[:, 588:]), 1e-6)
+    # (slices, h, w): 4-byte-only aligned strips (odd grid width), 16-byte aligned strips, a wide slice, every byte value
+    for (S, hh_, ww_) in ((3, 28, 42), (2, 448, 448), (1, 28, 1414), (5, 14, 70)):
+        px = torch.randint(0, 256, (S, hh_, ww_, 3), dtype=torch.uint8, device=dev)
+        px.view(-1)[:256] = torch.arange(256, dtype=torch.uint8, device=dev)
+        got = ops.im2col_norm(px, 14, 640)
+        # reference arithmetic on the CPU like torchvision's ToTensor/Normalize (true division; CUDA torch divides by reciprocal)
+        x = ((px.cpu().float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2)  # [S,3,h,w]
+        want = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588).to(dev)
+        ok &= report(f"im2col {S}x{hh_}x{ww_}", got[:, :588], want.bfloat16(), 0.0)   # bit-exact bf16
+        ok &= report("im2col pad", got[:, 588:], torch.zeros_like(got[:, 588:]), 0.0)
+    px = torch.randint(0, 256, (4, 32, 48, 3), dtype=torch.uint8, device=dev)       # another patch size / row pitch
+    got = ops.im2col_norm(px, 16, 768)
+    x = ((px.cpu().float() / 255 - 0.5) / 0.5).permute(0, 3, 1, 2)
+    ok &= report("im2col patch16", got, F.unfold(x, kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 768).to(dev).bfloat16(), 0.0)
     for D in (288, 1152, 2304):
         x = torch.randn(1000, D, device=dev) * 3 + 1
         g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
@@ -52,28 +59,33 @@ def stage_elementwise():
     h = ops.build_lm_input(src, emb, 12.0, vis)
     want = torch.stack([emb[5].float() * 12, vis[0], vis[1], vis[127], emb[511].float() * 12, emb[0].float() * 12])
     ok &= report("build_lm_input", h, want, 1e-6)
-    # pool
-    lens = [1, 5, 68, 300]
+    # pool: dims exercising every kernel instantiation (<=512, <=2048, 2304 exact, <=4096), empty and single-row sequences
+    lens = [1, 5, 68, 0, 300, 700]
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
-    hh = torch.randn(sum(lens), 2304, device=dev)
-    g = torch.randn(2304, device=dev)
-    for mode in ("wmean", "mean", "lasttoken", "cls"):
-        got = ops.pool_norm(hh, g, 1e-5, cu, mode, True)
-        outs = []
-        for i, n in enumerate(lens):
-            x = hh[cu[i]:cu[i + 1]]
-            x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * g
-            if mode == "wmean":
-                w = torch.arange(1, n + 1, device=dev).float()
-                r = (x * w[:, None]).sum(0) / w.sum()
-            elif mode == "mean":
-                r = x.mean(0)
-            elif mode == "lasttoken":
-                r = x[-1]
-            else:
-                r = x[0]
-            outs.append(F.normalize(r[None], dim=1)[0])
-        ok &= report(f"pool_norm {mode}", got, torch.stack(outs), 1e-5)
+    for D in (64, 576, 2304, 4096):
+        hh = torch.randn(sum(lens), D, device=dev)
+        g = torch.randn(D, device=dev)
+        for mode in ("wmean", "mean", "lasttoken", "cls"):
+            for normalize in (True, False):
+                got = ops.pool_norm(hh, g, 1e-5, cu, mode, normalize)
+                outs = []
+                for i, n in enumerate(lens):
+                    if n == 0:
+                        outs.append(torch.zeros(D, device=dev))
+                        continue
+                    x = hh[cu[i]:cu[i + 1]].double()
+                    x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * g.double()
+                    if mode == "wmean":
+                        w = torch.arange(1, n + 1, device=dev).double()
+                        r = (x * w[:, None]).sum(0) / w.sum()
+                    elif mode == "mean":
+                        r = x.mean(0)
+                    elif mode == "lasttoken":
+                        r = x[-1]
+                    else:
+                        r = x[0]
+                    outs.append((F.normalize(r[None], dim=1)[0] if normalize else r).float())
+                ok &= report(f"pool_norm D={D} {mode} norm={normalize}", got, torch.stack(outs), 2e-6)
     return ok
 
 

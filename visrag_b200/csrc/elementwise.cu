@@ -15,42 +15,67 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// im2col + normalise. One thread produces 8 consecutive output columns (one 16-byte store).
+// im2col + normalise. One CTA per (slice, patch row): the strip of `patch` full-width pixel rows is ONE contiguous,
+// 4-byte aligned span of patch*w*3 bytes; it is staged in shared memory with 16-byte (or 4-byte) coalesced loads,
+// then every thread builds 8 consecutive output columns (col = c*p*p + ky*p + kx) of one patch from shared memory and
+// writes them with one 16-byte store (a warp writes 512 contiguous bytes). ToTensor + Normalize(0.5, 0.5) is one
+// FFMA: bf16(fma(u, 2/255, -1)) == bf16((u/255 - 0.5)/0.5) for all 256 byte values (tests/test_gpu_kernels.py checks
+// every value), so the division of the fp32 reference is not needed for a bit-identical bf16 result.
 // ---------------------------------------------------------------------------------------------
-__global__ void im2col_norm_kernel(const uint8_t* __restrict__ px, int n_slices, int h, int w, int patch,
-                                   __nv_bfloat16* __restrict__ out, long long ldo) {
-    const int gh = h / patch, gw = w / patch;
+constexpr int IM2COL_THREADS = 256;
+
+__global__ void __launch_bounds__(IM2COL_THREADS)
+im2col_norm_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, int patch, __nv_bfloat16* __restrict__ out,
+                   long long ldo) {
+    extern __shared__ __align__(16) uint8_t strip[];  // [patch][w*3] + offset table [groups*8] (uint16)
+    const int w3 = gw * patch * 3;
+    const int strip_bytes = patch * w3;
     const int groups = static_cast<int>(ldo / 8);
-    const long long total = static_cast<long long>(n_slices) * gh * gw * groups;
     const int pp = patch * patch, kvalid = 3 * pp;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % groups);
-        const long long prow = i / groups;
-        const int pxi = static_cast<int>(prow % gw);
-        const int pyi = static_cast<int>((prow / gw) % gh);
-        const int s = static_cast<int>(prow / (static_cast<long long>(gw) * gh));
-        const uint8_t* img = px + static_cast<long long>(s) * h * w * 3;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = g * 8 + j;
-            if (col < kvalid) {
-                const int c = col / pp, rem = col - c * pp;
-                const int ky = rem / patch, kx = rem - ky * patch;
-                const int y = pyi * patch + ky, x = pxi * patch + kx;
-                const float u = static_cast<float>(img[(static_cast<long long>(y) * w + x) * 3 + c]);
-                v[j] = (u / 255.0f - 0.5f) / 0.5f;  // ToTensor then Normalize(0.5, 0.5), fp32 like torchvision
-            } else {
-                v[j] = 0.f;
-            }
+    unsigned short* off = reinterpret_cast<unsigned short*>(strip + ((strip_bytes + 15) & ~15));
+    // column -> (ky << 8 | kx*3 + c): position inside the strip relative to the patch's first pixel (0xFFFF = pad column)
+    for (int col = threadIdx.x; col < groups * 8; col += IM2COL_THREADS) {
+        unsigned short o = 0xFFFFu;
+        if (col < kvalid) {
+            const int c = col / pp, rem = col - c * pp;
+            const int ky = rem / patch, kx = rem - ky * patch;
+            o = static_cast<unsigned short>((ky << 8) | (kx * 3 + c));
         }
-        uint4 pk;
-        pk.x = pack_bf16x2(v[0], v[1]);
-        pk.y = pack_bf16x2(v[2], v[3]);
-        pk.z = pack_bf16x2(v[4], v[5]);
-        pk.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(out + prow * ldo + g * 8) = pk;
+        off[col] = o;
+    }
+    for (int sidx = blockIdx.x; sidx < n_strips; sidx += gridDim.x) {
+        const uint8_t* src = px + static_cast<long long>(sidx) * strip_bytes;
+        __syncthreads();  // previous strip fully consumed (and the offset table written, first iteration)
+        if (((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(strip_bytes)) & 15) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(strip);
+            for (int i = threadIdx.x; i < (strip_bytes >> 4); i += IM2COL_THREADS) d4[i] = __ldg(s4 + i);
+        } else if (((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(strip_bytes)) & 3) == 0) {
+            const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+            uint32_t* d1 = reinterpret_cast<uint32_t*>(strip);
+            for (int i = threadIdx.x; i < (strip_bytes >> 2); i += IM2COL_THREADS) d1[i] = __ldg(s1 + i);
+        } else {
+            for (int i = threadIdx.x; i < strip_bytes; i += IM2COL_THREADS) strip[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        __nv_bfloat16* orow0 = out + static_cast<long long>(sidx) * gw * ldo;
+        const int items = gw * groups;
+        for (int it = threadIdx.x; it < items; it += IM2COL_THREADS) {
+            const int p = it / groups, g = it - p * groups;
+            const uint4 o8 = *reinterpret_cast<const uint4*>(off + g * 8);
+            const uint8_t* base = strip + p * patch * 3;
+            const uint32_t ow[4] = {o8.x, o8.y, o8.z, o8.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t oa = ow[j] & 0xFFFFu, ob = ow[j] >> 16;
+                const uint32_t aa = (oa >> 8) * w3 + (oa & 0xFFu), ab = (ob >> 8) * w3 + (ob & 0xFFu);
+                const float va = oa == 0xFFFFu ? 0.f : fmaf(static_cast<float>(base[aa]), 2.0f / 255.0f, -1.0f);
+                const float vb = ob == 0xFFFFu ? 0.f : fmaf(static_cast<float>(base[ab]), 2.0f / 255.0f, -1.0f);
+                pk[j] = pack_bf16x2(va, vb);
+            }
+            *reinterpret_cast<uint4*>(orow0 + static_cast<long long>(p) * ldo + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
     }
 }
 
@@ -195,81 +220,118 @@ __global__ void build_lm_input_kernel(const int* __restrict__ src, int tokens, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Final RMSNorm + pooling + L2 normalise: one CTA per sequence.
-//   phase 1: warps compute 1/rms of every row of the sequence into shared memory;
-//   phase 2: thread-per-column weighted accumulation over the rows (coalesced across threads);
-//   phase 3: block reduction of the squared norm, normalise, write.
+// Final RMSNorm + pooling + L2 normalise: one thread-block CLUSTER of 8 CTAs per sequence, every row read from HBM once.
+//   phase 1: the cluster's 64 warps take the weighted rows round-robin; a warp holds its row in registers (VPL float4
+//            per lane), computes 1/rms and adds w_t/rms_t * x_t into its private register accumulator;
+//   phase 2: the 8 warps of a CTA are summed through shared memory (fixed order -> deterministic);
+//   phase 3: after a cluster barrier CTA 0 sums the 8 partial vectors over distributed shared memory, applies
+//            gamma / sum(w), reduces the squared norm, normalises and writes the embedding.
+// pooling: 0 = wmean (w_t = t+1), 1 = mean, 2 = lasttoken, 3 = cls (dense_retrieval_model.py:170-218).
 // ---------------------------------------------------------------------------------------------
 constexpr int POOL_THREADS = 256;
-constexpr int POOL_MAX_COLS_PER_THREAD = 16;  // dim <= 4096
+constexpr int POOL_WARPS = POOL_THREADS / 32;
+constexpr int POOL_CLUSTER = 8;
 
-__global__ void __launch_bounds__(POOL_THREADS)
+template <int VPL, bool EXACT>
+__global__ void __cluster_dims__(POOL_CLUSTER, 1, 1) __launch_bounds__(POOL_THREADS)
 pool_norm_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ gamma, float eps,
                  const int* __restrict__ cu, int dim, int pooling, int normalize, float* __restrict__ reps) {
-    extern __shared__ float inv_rms[];  // [len]
-    __shared__ float red[POOL_THREADS / 32];
+    extern __shared__ __align__(16) float pool_smem[];  // [POOL_WARPS][VPL*128] staging, reused as the CTA's partial vector
+    __shared__ float red[POOL_WARPS];
     __shared__ float total;
-    const int b = blockIdx.x;
+    constexpr int COLS = VPL * 128;
+    const int b = blockIdx.x / POOL_CLUSTER;
+    const unsigned rank = cluster_ctarank();
     const int begin = cu[b], len = cu[b + 1] - begin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = dim >> 2;
     float* out = reps + static_cast<long long>(b) * dim;
-    if (len <= 0) {
-        for (int c = threadIdx.x; c < dim; c += POOL_THREADS) out[c] = 0.f;
+    if (len <= 0) {  // uniform over the cluster: nobody reaches a cluster barrier
+        if (rank == 0)
+            for (int c = threadIdx.x; c < dim; c += POOL_THREADS) out[c] = 0.f;
         return;
     }
     int t_lo = 0, t_hi = len;  // rows that carry weight
     if (pooling == 2) t_lo = len - 1;
     if (pooling == 3) t_hi = 1;
-    for (int t = t_lo + warp; t < t_hi; t += POOL_THREADS / 32) {
+    float4 acc[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = t_lo + static_cast<int>(rank) * POOL_WARPS + warp; t < t_hi; t += POOL_CLUSTER * POOL_WARPS) {
         const float4* xr = reinterpret_cast<const float4*>(h + static_cast<long long>(begin + t) * ldh);
+        float4 v[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + i * 32;
+            v[i] = (EXACT || c < nvec) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float ss = 0.f;
-        for (int i = lane; i < (dim >> 2); i += 32) {
-            const float4 v = xr[i];
-            ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
         ss = warp_sum(ss);
-        if (lane == 0) inv_rms[t] = rsqrtf(ss / static_cast<float>(dim) + eps);
-    }
-    __syncthreads();
-    float acc[POOL_MAX_COLS_PER_THREAD];
-#pragma unroll
-    for (int j = 0; j < POOL_MAX_COLS_PER_THREAD; ++j) acc[j] = 0.f;
-    float wsum = 0.f;
-    for (int t = t_lo; t < t_hi; ++t) {
         const float w = (pooling == 0) ? static_cast<float>(t + 1) : 1.0f;
-        wsum += w;
-        const float s = w * inv_rms[t];
-        const float* xr = h + static_cast<long long>(begin + t) * ldh;
+        const float sc = w * rsqrtf(ss / static_cast<float>(dim) + eps);
 #pragma unroll
-        for (int j = 0; j < POOL_MAX_COLS_PER_THREAD; ++j) {
-            const int c = threadIdx.x + j * POOL_THREADS;
-            if (c < dim) acc[j] += s * xr[c];
+        for (int i = 0; i < VPL; ++i) {
+            acc[i].x += sc * v[i].x; acc[i].y += sc * v[i].y; acc[i].z += sc * v[i].z; acc[i].w += sc * v[i].w;
         }
     }
-    float sq = 0.f;
+    float4* stage = reinterpret_cast<float4*>(pool_smem) + warp * (COLS / 4);
 #pragma unroll
-    for (int j = 0; j < POOL_MAX_COLS_PER_THREAD; ++j) {
-        const int c = threadIdx.x + j * POOL_THREADS;
-        if (c < dim) {
-            acc[j] = acc[j] * gamma[c] / wsum;
-            sq += acc[j] * acc[j];
+    for (int i = 0; i < VPL; ++i) stage[lane + i * 32] = acc[i];
+    __syncthreads();
+    // CTA partial: column-wise sum over the 8 warps, written over warp 0's staging area
+    for (int c = threadIdx.x; c < COLS / 4; c += POOL_THREADS) {
+        float4 s4 = reinterpret_cast<const float4*>(pool_smem)[c];
+#pragma unroll
+        for (int wv = 1; wv < POOL_WARPS; ++wv) {
+            const float4 o = reinterpret_cast<const float4*>(pool_smem)[wv * (COLS / 4) + c];
+            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+        }
+        reinterpret_cast<float4*>(pool_smem)[c] = s4;  // column c of warp 0's area is read only by this thread
+    }
+    cluster_sync_all();
+    if (rank == 0) {
+        // sum(w) over the weighted rows in closed form (exact in fp32 for len < 4096; float otherwise)
+        const float n = static_cast<float>(t_hi - t_lo);
+        const float wsum = (pooling == 0) ? 0.5f * n * (n + 1.0f) : n;
+        const uint32_t my = smem_u32(pool_smem);
+        float sq = 0.f;
+        float4 mine[(COLS / 4 + POOL_THREADS - 1) / POOL_THREADS];
+#pragma unroll
+        for (int k = 0; k < (COLS / 4 + POOL_THREADS - 1) / POOL_THREADS; ++k) {
+            const int c = threadIdx.x + k * POOL_THREADS;
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nvec) {
+#pragma unroll
+                for (unsigned r = 0; r < POOL_CLUSTER; ++r) {
+                    const float4 o = ld_shared_cluster_f4(mapa_u32(my + c * 16, r));
+                    s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+                }
+                const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+                s4.x = s4.x * g.x / wsum; s4.y = s4.y * g.y / wsum; s4.z = s4.z * g.z / wsum; s4.w = s4.w * g.w / wsum;
+                sq += (s4.x * s4.x + s4.y * s4.y) + (s4.z * s4.z + s4.w * s4.w);
+            }
+            mine[k] = s4;
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s1 = 0.f;
+            for (int i = 0; i < POOL_WARPS; ++i) s1 += red[i];
+            total = s1;
+        }
+        __syncthreads();
+        const float inv = normalize ? 1.0f / fmaxf(sqrtf(total), 1e-12f) : 1.0f;
+#pragma unroll
+        for (int k = 0; k < (COLS / 4 + POOL_THREADS - 1) / POOL_THREADS; ++k) {
+            const int c = threadIdx.x + k * POOL_THREADS;
+            if (c < nvec)
+                reinterpret_cast<float4*>(out)[c] = make_float4(mine[k].x * inv, mine[k].y * inv, mine[k].z * inv, mine[k].w * inv);
         }
     }
-    sq = warp_sum(sq);
-    if (lane == 0) red[warp] = sq;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int i = 0; i < POOL_THREADS / 32; ++i) s += red[i];
-        total = s;
-    }
-    __syncthreads();
-    const float inv = normalize ? 1.0f / fmaxf(sqrtf(total), 1e-12f) : 1.0f;
-#pragma unroll
-    for (int j = 0; j < POOL_MAX_COLS_PER_THREAD; ++j) {
-        const int c = threadIdx.x + j * POOL_THREADS;
-        if (c < dim) out[c] = acc[j] * inv;
-    }
+    cluster_sync_all();  // the peers' shared memory must stay alive until CTA 0 has read it
 }
 
 static int grid_for(long long work_items, int per_block) {
@@ -291,9 +353,20 @@ extern "C" int vr_im2col_norm(const uint8_t* pixels, int32_t n_slices, int32_t h
                "vr_im2col_norm: bad geometry n=%d h=%d w=%d patch=%d", n_slices, h, w, patch);
     VR_REQUIRE(ldo % 8 == 0 && ldo >= 3 * patch * patch, "vr_im2col_norm: ldo=%lld must be a multiple of 8 and >= %d",
                (long long)ldo, 3 * patch * patch);
-    const long long total = static_cast<long long>(n_slices) * (h / patch) * (w / patch) * (ldo / 8);
-    im2col_norm_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        pixels, n_slices, h, w, patch, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+    VR_REQUIRE(patch <= 85, "vr_im2col_norm: patch=%d exceeds 85", patch);
+    const int gw = w / patch;
+    const long long n_strips = static_cast<long long>(n_slices) * (h / patch);
+    VR_REQUIRE(n_strips < (1ll << 31), "vr_im2col_norm: too many patch rows");
+    const size_t smem = ((static_cast<size_t>(patch) * w * 3 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(ldo) * 2;
+    VR_REQUIRE(smem <= 200 * 1024, "vr_im2col_norm: a %d-pixel-wide slice does not fit the %d-row strip buffer", w, patch);
+    static unsigned long long configured = 0;
+    if (first_use_on_device(&configured))
+        VR_CHECK_CUDA(cudaFuncSetAttribute(im2col_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long blocks = n_strips;
+    const long long cap = static_cast<long long>(num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    im2col_norm_kernel<<<static_cast<int>(blocks), IM2COL_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        pixels, static_cast<int>(n_strips), gw, patch, reinterpret_cast<__nv_bfloat16*>(out), ldo);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -347,12 +420,27 @@ extern "C" int vr_build_lm_input(const int32_t* src, int32_t tokens, int32_t dim
 extern "C" int vr_pool_norm(const float* h, int64_t ldh, const float* gamma, float eps, const int32_t* cu, int32_t batch,
                             int32_t dim, int32_t pooling, int32_t normalize, float* reps, void* stream) {
     VR_REQUIRE(h && gamma && cu && reps, "vr_pool_norm: null pointer");
-    VR_REQUIRE(batch > 0 && dim > 0 && dim % 4 == 0 && dim <= POOL_THREADS * POOL_MAX_COLS_PER_THREAD && ldh % 4 == 0,
+    VR_REQUIRE(batch > 0 && dim > 0 && dim % 4 == 0 && dim <= 4096 && ldh % 4 == 0,
                "vr_pool_norm: bad shape batch=%d dim=%d", batch, dim);
     VR_REQUIRE(pooling >= 0 && pooling <= 3, "vr_pool_norm: pooling must be 0..3");
-    const int smem = 2048 * sizeof(float) * 4;  // sequences up to 8192 tokens
-    pool_norm_kernel<<<batch, POOL_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(h, ldh, gamma, eps, cu, dim,
-                                                                                          pooling, normalize, reps);
+    VR_REQUIRE((reinterpret_cast<uintptr_t>(h) & 15) == 0 && (reinterpret_cast<uintptr_t>(reps) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gamma) & 15) == 0,
+               "vr_pool_norm: h, gamma and reps must be 16-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>(batch) * POOL_CLUSTER;
+#define VR_POOL_LAUNCH(VPL, EXACT)                                                                                        \
+    do {                                                                                                                  \
+        const int smem = POOL_WARPS * (VPL) * 128 * static_cast<int>(sizeof(float));                                      \
+        static unsigned long long configured = 0;                                                                         \
+        if (first_use_on_device(&configured))                                                                             \
+            VR_CHECK_CUDA(cudaFuncSetAttribute(pool_norm_kernel<VPL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        pool_norm_kernel<VPL, EXACT><<<grid, POOL_THREADS, smem, s>>>(h, ldh, gamma, eps, cu, dim, pooling, normalize, reps); \
+    } while (0)
+    if (dim == 2304) VR_POOL_LAUNCH(18, true);
+    else if (dim <= 512) VR_POOL_LAUNCH(4, false);
+    else if (dim <= 2048) VR_POOL_LAUNCH(16, false);
+    else VR_POOL_LAUNCH(32, false);
+#undef VR_POOL_LAUNCH
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -15,7 +15,7 @@
 //
 // Tie rule everywhere: higher score first, then lower doc id.
 #include "common.h"
-#include "gemm.cuh"
+#include "gemm2.cuh"
 #include <math.h>
 
 namespace vr {
@@ -23,17 +23,35 @@ namespace vr {
 constexpr int SC_KT = 16;    // candidates kept per list
 constexpr int SC_BN = 256;   // docs per tile
 
+// Work decomposition of the filter ("stream-K" over the doc axis): the unit of work is one 256-query x 256-doc tile;
+// units are numbered u = b*T + t (b = 256-query block, t = doc tile, T = doc tiles) and CTA pair p owns the contiguous
+// span [p*chunk, (p+1)*chunk): every pair gets the same number of tiles (no wave quantisation - the round-1 kernel ran
+// 79 CTAs on 148 SMs for 10k queries), and a query block is touched by at most floor((T-1)/chunk)+2 pairs, each of which
+// emits ONE candidate list per query ("piece"), so the exact rescoring stays small.
 struct ScoreArgs {
     int nq;
     long long nd;
     int dim;
-    int ranges;
-    float* cand_scores;  // [nq, ranges*2*SC_KT]
+    int lists;         // candidate lists per query (>= pieces of any query block; unused ones are written empty)
+    int T;             // doc tiles
+    int chunk;         // units per CTA pair
+    long long W;       // total units
+    float* cand_scores;  // [nq, lists*SC_KT]
     int* cand_ids;
 };
 
+struct Score2Cfg {
+    static constexpr int STAGES = 6;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // this CTA's 128 query rows
+    static constexpr int B_BYTES = 128 * GEMM_BK * 2;       // this CTA's half of the 256 docs
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+    static constexpr int MERGE_BYTES = 4 * SC_KT * 32 * 8;  // per quarter: 16 x 32 (score, id) pairs
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + MERGE_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 512;
+};
+
 __device__ __forceinline__ void topk_insert(float (&sc)[SC_KT], int (&id)[SC_KT], float v, int i) {
-    // precondition: v > sc[SC_KT-1]; lists are sorted descending, ties keep the earlier (lower) doc id first
+    // precondition: v > sc[SC_KT-1]; lists are sorted descending, ties keep the earlier entry first
     sc[SC_KT - 1] = v;
     id[SC_KT - 1] = i;
 #pragma unroll
@@ -48,16 +66,26 @@ __device__ __forceinline__ void topk_insert(float (&sc)[SC_KT], int (&id)[SC_KT]
     }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// CTA pair (tcgen05 cta_group::2): 256 queries x 256 docs per MMA tile, fp16 operands, fp32 accumulators in the TMEM of
+// both CTAs (two stages). Roles as in gemm2.cuh; the epilogue threads (one query row each, the two column halves of a
+// row in two warps) keep a sorted top-16 in registers over all tiles of a piece, merge the halves through shared memory
+// (top-16 of the union: its tail bounds everything either half dropped) and write one list per (query, piece).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                     const ScoreArgs g) {
-    using Cfg = GemmCfg<SC_BN>;
+    using Cfg = Score2Cfg;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* merge_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [4][SC_KT][32]
+    int* merge_i = reinterpret_cast<int*>(merge_s + 4 * SC_KT * 32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::MERGE_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -65,12 +93,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x, qb = blockIdx.y;
-    const long long doc_tiles = (g.nd + SC_BN - 1) / SC_BN;
-    const int t_begin = static_cast<int>(doc_tiles * r / g.ranges);
-    const int t_end = static_cast<int>(doc_tiles * (r + 1) / g.ranges);
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const long long u0 = static_cast<long long>(pair) * g.chunk;
+    const long long u1 = min(g.W, u0 + g.chunk);
     const int num_kb = (g.dim + GEMM_BK - 1) / GEMM_BK;
-    const int m0 = qb * GEMM_BM;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -78,18 +105,19 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full_bar[i], 1);
+            mbar_init(&full_bar[i], 2);   // one arrive.expect_tx per CTA (used in the leader only)
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
+            mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS);  // used in the leader only
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    cluster_sync_all();
+    if (warp == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -97,57 +125,107 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
+            int b = static_cast<int>(u0 / g.T), t = static_cast<int>(u0 - static_cast<long long>(b) * g.T);
+            for (long long u = u0; u < u1; ++u) {
+                const int m0 = b * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+                const int n0 = t * SC_BN + static_cast<int>(rank) * 128;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * Cfg::A_BYTES, kb * GEMM_BK, m0);
-                    tma_load_2d(&tmap_d, &full_bar[stage], smem_b + stage * Cfg::B_BYTES, kb * GEMM_BK, t * SC_BN);
-                    tma_load_2d(&tmap_d, &full_bar[stage], smem_b + stage * Cfg::B_BYTES + Cfg::B_BYTES / 2, kb * GEMM_BK,
-                                t * SC_BN + 128);
+                    const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    mbar_expect_tx_cluster(lfull, Cfg::STAGE_BYTES);
+                    tma_load_2d_2sm(&tmap_q, lfull, smem_a + stage * Cfg::A_BYTES, kb * GEMM_BK, m0);
+                    tma_load_2d_2sm(&tmap_d, lfull, smem_b + stage * Cfg::B_BYTES, kb * GEMM_BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++t == g.T) { t = 0; ++b; }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // whole warp, warp-uniform control flow, one elected lane issues (see gemm.cuh)
+            constexpr uint32_t idesc = make_idesc_f16(2 * GEMM_BM, SC_BN, 0 /*fp16*/, 0, 0);
+            const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128);
+            const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (long long u = u0; u < u1; ++u, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * SC_BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = desc_hi | static_cast<uint64_t>(a_lo0 + stage * (Cfg::A_BYTES >> 4));
+                        const uint64_t bd = desc_hi | static_cast<uint64_t>(b_lo0 + stage * (Cfg::B_BYTES >> 4));
+                        umma_f16_ss_2sm(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+                        umma_f16_ss_2sm(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                        umma_f16_ss_2sm(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                        umma_f16_ss_2sm(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                        umma_commit_2sm(&empty_bar[stage], 3);  // frees the slot in BOTH CTAs
+                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc], 3);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // whole warp, warp-uniform control flow, one elected lane issues (see gemm.cuh)
-        constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, SC_BN, 0 /*fp16*/, 0, 0);
-        const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128);
-        const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int t = t_begin; t < t_end; ++t, ++it) {
-            const int acc = it & 1;
-            mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * SC_BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t ad = desc_hi | static_cast<uint64_t>(a_lo0 + stage * (Cfg::A_BYTES >> 4));
-                    const uint64_t bd = desc_hi | static_cast<uint64_t>(b_lo0 + stage * (Cfg::B_BYTES >> 4));
-                    umma_f16_ss(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
-                    umma_f16_ss(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                    umma_f16_ss(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                    umma_f16_ss(d_tmem, ad + 6, bd + 6, idesc, 1u);
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
     } else if (warp >= 4) {
         const int quarter = warp & 3, half = (warp - 4) >> 2;
-        const int row = m0 + quarter * 32 + lane;
         float sc[SC_KT];
         int id[SC_KT];
 #pragma unroll
         for (int j = 0; j < SC_KT; ++j) { sc[j] = -INFINITY; id[j] = -1; }
+        float* ms = merge_s + quarter * SC_KT * 32;
+        int* mi = merge_i + quarter * SC_KT * 32;
+        // one candidate list per (query row, piece): merge the two column halves, write, pad the row's unused lists
+        auto flush = [&](int b, bool last_piece) {
+            if (half == 1) {
+#pragma unroll
+                for (int j = 0; j < SC_KT; ++j) { ms[j * 32 + lane] = sc[j]; mi[j * 32 + lane] = id[j]; }
+            }
+            named_bar_sync(1 + quarter, 64);
+            if (half == 0) {
+#pragma unroll
+                for (int j = 0; j < SC_KT; ++j) {
+                    const float v = ms[j * 32 + lane];
+                    if (v > sc[SC_KT - 1]) topk_insert(sc, id, v, mi[j * 32 + lane]);
+                }
+            }
+            named_bar_sync(1 + quarter, 64);
+            const int row = b * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32 + lane;
+            if (half == 0 && row < g.nq) {
+                const int slot = pair - static_cast<int>(static_cast<long long>(b) * g.T / g.chunk);
+                long long base = (static_cast<long long>(row) * g.lists + slot) * SC_KT;
+#pragma unroll
+                for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
+                    *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
+                        make_float4(sc[j4 * 4], sc[j4 * 4 + 1], sc[j4 * 4 + 2], sc[j4 * 4 + 3]);
+                    *reinterpret_cast<int4*>(g.cand_ids + base + j4 * 4) =
+                        make_int4(id[j4 * 4], id[j4 * 4 + 1], id[j4 * 4 + 2], id[j4 * 4 + 3]);
+                }
+                if (last_piece) {
+                    for (int s2 = slot + 1; s2 < g.lists; ++s2) {
+                        base += SC_KT;
+#pragma unroll
+                        for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
+                            *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
+                                make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                            *reinterpret_cast<int4*>(g.cand_ids + base + j4 * 4) = make_int4(-1, -1, -1, -1);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SC_KT; ++j) { sc[j] = -INFINITY; id[j] = -1; }
+        };
+        const uint32_t ltempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t ltempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+        int b = static_cast<int>(u0 / g.T), t = static_cast<int>(u0 - static_cast<long long>(b) * g.T);
         int it = 0;
-        for (int t = t_begin; t < t_end; ++t, ++it) {
+        for (long long u = u0; u < u1; ++u, ++it) {
             const int acc = it & 1;
             mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
             tc_fence_after();
@@ -161,7 +239,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (c == 3) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) mbar_arrive_cluster(acc ? ltempty1 : ltempty0);
                 }
                 const long long c0 = col_base + c * 32;
 #pragma unroll
@@ -170,23 +248,19 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     if (s > sc[SC_KT - 1] && c0 + j < g.nd) topk_insert(sc, id, s, static_cast<int>(c0 + j));
                 }
             }
-        }
-        if (row < g.nq) {
-            const long long base = (static_cast<long long>(row) * g.ranges * 2 + r * 2 + half) * SC_KT;
-#pragma unroll
-            for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
-                *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
-                    make_float4(sc[j4 * 4], sc[j4 * 4 + 1], sc[j4 * 4 + 2], sc[j4 * 4 + 3]);
-                *reinterpret_cast<int4*>(g.cand_ids + base + j4 * 4) =
-                    make_int4(id[j4 * 4], id[j4 * 4 + 1], id[j4 * 4 + 2], id[j4 * 4 + 3]);
+            if (++t == g.T) {  // the query block is finished: this pair holds its last piece
+                flush(b, true);
+                t = 0;
+                ++b;
             }
         }
+        if (t != 0) flush(b, false);  // the span ends inside a query block: the next pair continues it
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // the peer may still be arriving on this CTA's barriers until here
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -440,15 +514,60 @@ __global__ void f32_to_f16_rows_kernel(const float* __restrict__ src, long long 
     }
 }
 
-static int score_ranges_for(int nq, long long nd) {
-    const int qb = (nq + GEMM_BM - 1) / GEMM_BM;
-    long long tiles = (nd + SC_BN - 1) / SC_BN;
-    long long r = num_sms() / qb;
-    if (r < 1) r = 1;
-    if (r > tiles) r = tiles;
-    if (r < 1) r = 1;
-    return static_cast<int>(r);
+// Co-resident CTA pairs of the filter kernel on the current device (GPCs with an odd number of usable SMs cannot pair
+// all of them; a persistent kernel must not launch more clusters than fit at once).
+static int score_pairs() {
+    static int cached[64] = {};
+    const int dev = current_device();
+    const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+    if (cached[slot] == 0) {
+        int n = 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / 2 * 2);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Score2Cfg::SMEM_BYTES;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        if (dev < 0 ||
+            cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Score2Cfg::SMEM_BYTES) != cudaSuccess ||
+            cudaOccupancyMaxActiveClusters(&n, score_filter_kernel, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = num_sms() / 2;
+        }
+        cached[slot] = n < num_sms() / 2 ? n : num_sms() / 2;
+    }
+    return cached[slot];
 }
+
+struct ScorePlan {
+    int T, chunk, lists, pairs;
+    long long W;
+};
+
+static ScorePlan score_plan(int nq, long long nd) {
+    constexpr int MIN_CHUNK = 4;  // tiles per pair below which the pipeline fill and the extra candidate lists dominate
+    ScorePlan p;
+    const int qb = (nq + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    p.T = static_cast<int>((nd + SC_BN - 1) / SC_BN);
+    p.W = static_cast<long long>(qb) * p.T;
+    const int P = score_pairs();
+    long long chunk = (p.W + P - 1) / P;
+    if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
+    p.chunk = static_cast<int>(chunk);
+    p.pairs = static_cast<int>((p.W + chunk - 1) / chunk);
+    int pieces = 1;
+    for (int b = 0; b < qb; ++b) {
+        const long long first = static_cast<long long>(b) * p.T / chunk, last = (static_cast<long long>(b + 1) * p.T - 1) / chunk;
+        if (last - first + 1 > pieces) pieces = static_cast<int>(last - first + 1);
+    }
+    p.lists = 2 * ((pieces + 1) / 2);
+    return p;
+}
+
+static int score_ranges_for(int nq, long long nd) { return score_plan(nq, nd).lists / 2; }
 
 }  // namespace vr
 
@@ -475,8 +594,10 @@ extern "C" int vr_score_filter(const void* q_f16, int32_t nq, const void* d_f16,
     VR_REQUIRE(q_f16 && d_f16 && cand_scores && cand_ids, "vr_score_filter: null pointer");
     VR_REQUIRE(nq > 0 && nd > 0 && nd < 2147483647ll && dim % 8 == 0, "vr_score_filter: bad shape nq=%d nd=%lld dim=%d", nq,
                (long long)nd, dim);
-    VR_REQUIRE(ranges == score_ranges_for(nq, nd), "vr_score_filter: ranges must come from vr_score_ranges()");
-    using Cfg = GemmCfg<SC_BN>;
+    VR_REQUIRE(nq < (1 << 30), "vr_score_filter: too many queries");
+    const ScorePlan plan = score_plan(nq, nd);
+    VR_REQUIRE(ranges * 2 == plan.lists, "vr_score_filter: ranges must come from vr_score_ranges()");
+    using Cfg = Score2Cfg;
     CUtensorMap tq, td;
     if (int rc = make_tmap_2d(&tq, q_f16, nq, dim, dim, GEMM_BM, GEMM_BK, 128, false)) return rc;
     if (int rc = make_tmap_2d(&td, d_f16, nd, dim, dim, 128, GEMM_BK, 128, false)) return rc;
@@ -484,9 +605,9 @@ extern "C" int vr_score_filter(const void* q_f16, int32_t nq, const void* d_f16,
     if (first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     ScoreArgs g;
-    g.nq = nq; g.nd = nd; g.dim = dim; g.ranges = ranges; g.cand_scores = cand_scores; g.cand_ids = cand_ids;
-    dim3 grid(ranges, (nq + GEMM_BM - 1) / GEMM_BM);
-    score_filter_kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, td, g);
+    g.nq = nq; g.nd = nd; g.dim = dim; g.lists = plan.lists; g.T = plan.T; g.chunk = plan.chunk; g.W = plan.W;
+    g.cand_scores = cand_scores; g.cand_ids = cand_ids;
+    score_filter_kernel<<<2 * plan.pairs, GEMM_THREADS, Cfg::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, td, g);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
