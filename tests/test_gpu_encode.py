@@ -351,3 +351,36 @@ def test_build_from_checkpoint_directory(tmp_path):
 
     with pytest.raises(NotImplementedError):
         config_from_hf(bad)
+
+
+def test_cuda_graph_path_is_bit_identical_to_eager_launches():
+    """Small batches replay a captured CUDA graph of the same C-ABI launches (second sighting of a shape signature
+    captures, later ones replay). Pages: new pixel content through the same graph; queries: different texts share a
+    graph through the padded token buckets (one dummy sequence). Everything must equal the eager engine bit for bit."""
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.encoder import VisRAGEngine
+    from visrag_b200.tokenizer_stub import StubTokenizer
+    from visrag_b200.weights import random_state_dict
+
+    cfg = VisRAGConfig.tiny()
+    sd = random_state_dict(cfg, 5)
+    eager = VisRAGEngine(cfg, sd, cuda_graphs=False)
+    graphed = VisRAGEngine(cfg, sd, cuda_graphs=True)
+    tok = StubTokenizer(cfg.vocab)
+    sizes = [(448, 448), (700, 900), (448, 448)]
+    for seed in (1, 2, 3, 4):                       # same shapes, fresh pixels: eager, capture, replay, replay
+        pages = synth_pages(sizes, seed)
+        assert torch.equal(graphed.encode([""] * 3, pages, tok), eager.encode([""] * 3, pages, tok)), seed
+    assert graphed.graph_stats == {"captured": 1, "replayed": 3, "eager": 1}
+    queries = ["revenue table 2020", "a much longer question about the climate chart on page seven of the report",
+               "cat", "dog on a sofa", "what is the total", "x"]
+    for rep in range(2):
+        for n in (1, 2, 3):                          # batches of different composition, several token buckets
+            for i in range(0, len(queries) - n + 1):
+                q = queries[i:i + n]
+                for pooling in ("wmean", "lasttoken"):
+                    a = graphed.encode(q, [None] * n, tok, pooling=pooling)
+                    b = eager.encode(q, [None] * n, tok, pooling=pooling)
+                    assert a.shape == (n, cfg.hidden) and torch.equal(a, b), (q, pooling)
+    assert graphed.graph_stats["replayed"] > graphed.graph_stats["captured"] > 1
+    assert eager.graph_stats == {"captured": 0, "replayed": 0, "eager": 0}

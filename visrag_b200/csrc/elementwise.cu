@@ -79,6 +79,78 @@ im2col_norm_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, int pat
     }
 }
 
+// Patch 14 (the only size the model uses): one thread per (patch, pixel row) = 42 contiguous source bytes -> three runs
+// of 14 bf16 (one per channel) in the patch's output row. Bytes become floats with one PRMT each (0x4B0000xx = 2^23 + u,
+// then - 2^23: exact, and no I2F on the quarter-rate conversion pipe), the output rows of the strip are assembled in
+// shared memory and leave with ONE bulk (TMA) store per strip while the next strip is being loaded.
+constexpr int IM2COL14_THREADS = 256;
+
+__global__ void __launch_bounds__(IM2COL14_THREADS)
+im2col_norm14_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, __nv_bfloat16* __restrict__ out, int ldo) {
+    constexpr int P = 14, RUN = P * 3;  // 42 bytes per (patch, pixel row)
+    extern __shared__ __align__(16) uint8_t smem14[];
+    const int w3 = gw * RUN;
+    const int strip_bytes = P * w3;
+    const int in_bytes = (strip_bytes + 8 + 15) & ~15;  // + 8: the last item's 12-word window reads past its 42 bytes
+    uint8_t* strip = smem14;
+    uint8_t* tile = smem14 + in_bytes;  // [gw][ldo] bf16
+    const int tile_bytes = gw * ldo * 2;
+    // zero the padding columns once: they are never written again
+    for (int i = threadIdx.x; i < gw * (ldo - 3 * P * P); i += IM2COL14_THREADS) {
+        const int p = i / (ldo - 3 * P * P), c = i - p * (ldo - 3 * P * P);
+        reinterpret_cast<__nv_bfloat16*>(tile)[p * ldo + 3 * P * P + c] = __float2bfloat16(0.f);
+    }
+    for (int i = strip_bytes + threadIdx.x; i < in_bytes; i += IM2COL14_THREADS) strip[i] = 0;
+    for (int sidx = blockIdx.x; sidx < n_strips; sidx += gridDim.x) {
+        const uint8_t* src = px + static_cast<long long>(sidx) * strip_bytes;
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile free again
+        __syncthreads();
+        if (((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(strip_bytes)) & 15) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(strip);
+            for (int i = threadIdx.x; i < (strip_bytes >> 4); i += IM2COL14_THREADS) d4[i] = __ldcs(s4 + i);
+        } else {  // 588*gw bytes at a multiple of that: always 4-byte aligned
+            const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+            uint32_t* d1 = reinterpret_cast<uint32_t*>(strip);
+            for (int i = threadIdx.x; i < (strip_bytes >> 2); i += IM2COL14_THREADS) d1[i] = __ldcs(s1 + i);
+        }
+        __syncthreads();
+        for (int it = threadIdx.x; it < gw * P; it += IM2COL14_THREADS) {
+            const int p = it / P, ky = it - p * P;
+            const int off = ky * w3 + p * RUN;  // even
+            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(strip + (off & ~3));
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) w[i] = wsrc[i];
+            if (off & 2) {
+#pragma unroll
+                for (int i = 0; i < 11; ++i) w[i] = __funnelshift_r(w[i], w[i + 1], 16);
+            }
+            uint32_t* dst = reinterpret_cast<uint32_t*>(tile + (p * ldo + ky * P) * 2);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                for (int i = 0; i < P / 2; ++i) {
+                    const int k0 = (2 * i) * 3 + c, k1 = (2 * i + 1) * 3 + c;  // byte index of pixel 2i / 2i+1, channel c
+                    const float f0 = __uint_as_float(__byte_perm(w[k0 >> 2], 0x4B000000u, 0x7540 | (k0 & 3))) - 8388608.0f;
+                    const float f1 = __uint_as_float(__byte_perm(w[k1 >> 2], 0x4B000000u, 0x7540 | (k1 & 3))) - 8388608.0f;
+                    dst[c * (P * P / 2) + i] = pack_bf16x2(fmaf(f0, 2.0f / 255.0f, -1.0f), fmaf(f1, 2.0f / 255.0f, -1.0f));
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __nv_bfloat16* gdst = out + static_cast<long long>(sidx) * gw * ldo;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(tile)),
+                         "r"(tile_bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm / RMSNorm: one warp per row, dim % 4 == 0.
 // ---------------------------------------------------------------------------------------------
@@ -221,14 +293,14 @@ __global__ void build_lm_input_kernel(const int* __restrict__ src, int tokens, i
 
 // ---------------------------------------------------------------------------------------------
 // Final RMSNorm + pooling + L2 normalise: one thread-block CLUSTER of 8 CTAs per sequence, every row read from HBM once.
-//   phase 1: the cluster's 64 warps take the weighted rows round-robin; a warp holds its row in registers (VPL float4
+//   phase 1: the cluster's 32 warps take the weighted rows round-robin; a warp holds its row in registers (VPL float4
 //            per lane), computes 1/rms and adds w_t/rms_t * x_t into its private register accumulator;
-//   phase 2: the 8 warps of a CTA are summed through shared memory (fixed order -> deterministic);
+//   phase 2: the 4 warps of a CTA are summed through shared memory (fixed order -> deterministic);
 //   phase 3: after a cluster barrier CTA 0 sums the 8 partial vectors over distributed shared memory, applies
 //            gamma / sum(w), reduces the squared norm, normalises and writes the embedding.
 // pooling: 0 = wmean (w_t = t+1), 1 = mean, 2 = lasttoken, 3 = cls (dense_retrieval_model.py:170-218).
 // ---------------------------------------------------------------------------------------------
-constexpr int POOL_THREADS = 256;
+constexpr int POOL_THREADS = 128;  // 4 warps x ~164 registers: three CTAs per SM (256 threads left one)
 constexpr int POOL_WARPS = POOL_THREADS / 32;
 constexpr int POOL_CLUSTER = 8;
 
@@ -357,15 +429,31 @@ extern "C" int vr_im2col_norm(const uint8_t* pixels, int32_t n_slices, int32_t h
     const int gw = w / patch;
     const long long n_strips = static_cast<long long>(n_slices) * (h / patch);
     VR_REQUIRE(n_strips < (1ll << 31), "vr_im2col_norm: too many patch rows");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long blocks = n_strips;
+    if (patch == 14 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(pixels) & 3) == 0) {
+        const size_t smem14 = ((static_cast<size_t>(14) * w * 3 + 8 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(gw) * ldo * 2;
+        if (smem14 <= 200 * 1024) {
+            static unsigned long long configured14 = 0;
+            if (first_use_on_device(&configured14))
+                VR_CHECK_CUDA(cudaFuncSetAttribute(im2col_norm14_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            const long long per_sm = (200 * 1024) / static_cast<long long>(smem14) < 4 ? (200 * 1024) / static_cast<long long>(smem14) : 4;
+            const long long cap14 = static_cast<long long>(num_sms()) * (per_sm < 1 ? 1 : per_sm);
+            if (blocks > cap14) blocks = cap14;
+            im2col_norm14_kernel<<<static_cast<int>(blocks), IM2COL14_THREADS, smem14, st>>>(
+                pixels, static_cast<int>(n_strips), gw, reinterpret_cast<__nv_bfloat16*>(out), static_cast<int>(ldo));
+            VR_CHECK_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const size_t smem = ((static_cast<size_t>(patch) * w * 3 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(ldo) * 2;
     VR_REQUIRE(smem <= 200 * 1024, "vr_im2col_norm: a %d-pixel-wide slice does not fit the %d-row strip buffer", w, patch);
     static unsigned long long configured = 0;
     if (first_use_on_device(&configured))
         VR_CHECK_CUDA(cudaFuncSetAttribute(im2col_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    long long blocks = n_strips;
     const long long cap = static_cast<long long>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
-    im2col_norm_kernel<<<static_cast<int>(blocks), IM2COL_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+    im2col_norm_kernel<<<static_cast<int>(blocks), IM2COL_THREADS, smem, st>>>(
         pixels, static_cast<int>(n_strips), gw, patch, reinterpret_cast<__nv_bfloat16*>(out), ldo);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;

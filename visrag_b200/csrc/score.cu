@@ -22,20 +22,25 @@ namespace vr {
 
 constexpr int SC_KT = 16;    // candidates kept per list
 constexpr int SC_BN = 256;   // docs per tile
+constexpr int SC_MAX_RANGES = 64;  // doc ranges (= candidate lists per query) the filter may use
 
-// Work decomposition of the filter ("stream-K" over the doc axis): the unit of work is one 256-query x 256-doc tile;
-// units are numbered u = b*T + t (b = 256-query block, t = doc tile, T = doc tiles) and CTA pair p owns the contiguous
-// span [p*chunk, (p+1)*chunk): every pair gets the same number of tiles (no wave quantisation - the round-1 kernel ran
-// 79 CTAs on 148 SMs for 10k queries), and a query block is touched by at most floor((T-1)/chunk)+2 pairs, each of which
-// emits ONE candidate list per query ("piece"), so the exact rescoring stays small.
+// Work decomposition of the filter: the unit of work is one 256-query x 256-doc MMA tile (one CTA pair). The doc axis
+// is cut into R equal ranges; item i = r*QB + b (QB = 256-query blocks) is the sweep of query block b over doc range r,
+// and pair p runs items p, p+P, p+2P, ... Items have the same length and start together, so all pairs of a wave walk
+// their doc range in lockstep: at any moment the whole GPU reads at most ceil(P/QB)+1 distinct doc tiles and every doc
+// tile is fetched from HBM once and then served to the other query blocks from L2. (A contiguous "stream-K" split of
+// the b-major tile list balances perfectly but de-phases the pairs: measured 23 GB of DRAM reads instead of 0.6 GB
+// and 6.0 ms instead of the ~4 ms this layout takes at 10 k x 125 k.) R is chosen by the host to fill whole waves
+// (score_plan); every item emits ONE 16-entry candidate list per query, so a query has R lists.
 struct ScoreArgs {
     int nq;
     long long nd;
     int dim;
-    int lists;         // candidate lists per query (>= pieces of any query block; unused ones are written empty)
+    int lists;         // candidate lists per query (>= R; the ones beyond R are written empty)
     int T;             // doc tiles
-    int chunk;         // units per CTA pair
-    long long W;       // total units
+    int R;             // doc ranges
+    int QB;            // 256-query blocks
+    int items;         // R * QB
     float* cand_scores;  // [nq, lists*SC_KT]
     int* cand_ids;
 };
@@ -95,9 +100,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1;
-    const long long u0 = static_cast<long long>(pair) * g.chunk;
-    const long long u1 = min(g.W, u0 + g.chunk);
+    const int num_pairs = gridDim.x >> 1;
     const int num_kb = (g.dim + GEMM_BK - 1) / GEMM_BK;
+    // item -> (query block b, doc tiles [t0, t1))
+    auto item_b = [&](int item) { return item % g.QB; };
+    auto item_t0 = [&](int item) { return static_cast<int>(static_cast<long long>(g.T) * (item / g.QB) / g.R); };
+    auto item_t1 = [&](int item) { return static_cast<int>(static_cast<long long>(g.T) * (item / g.QB + 1) / g.R); };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -125,19 +133,20 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int b = static_cast<int>(u0 / g.T), t = static_cast<int>(u0 - static_cast<long long>(b) * g.T);
-            for (long long u = u0; u < u1; ++u) {
-                const int m0 = b * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
-                const int n0 = t * SC_BN + static_cast<int>(rank) * 128;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                    mbar_expect_tx_cluster(lfull, Cfg::STAGE_BYTES);
-                    tma_load_2d_2sm(&tmap_q, lfull, smem_a + stage * Cfg::A_BYTES, kb * GEMM_BK, m0);
-                    tma_load_2d_2sm(&tmap_d, lfull, smem_b + stage * Cfg::B_BYTES, kb * GEMM_BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int item = pair; item < g.items; item += num_pairs) {
+                const int m0 = item_b(item) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+                const int t1 = item_t1(item);
+                for (int t = item_t0(item); t < t1; ++t) {
+                    const int n0 = t * SC_BN + static_cast<int>(rank) * 128;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        mbar_expect_tx_cluster(lfull, Cfg::STAGE_BYTES);
+                        tma_load_2d_2sm(&tmap_q, lfull, smem_a + stage * Cfg::A_BYTES, kb * GEMM_BK, m0);
+                        tma_load_2d_2sm(&tmap_d, lfull, smem_b + stage * Cfg::B_BYTES, kb * GEMM_BK, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
-                if (++t == g.T) { t = 0; ++b; }
             }
         }
     } else if (warp == 1) {
@@ -148,8 +157,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (long long u = u0; u < u1; ++u, ++it) {
+            int units = 0;  // tiles this pair computes
+            for (int item = pair; item < g.items; item += num_pairs) units += item_t1(item) - item_t0(item);
+            for (int it = 0; it < units; ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -180,8 +190,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int j = 0; j < SC_KT; ++j) { sc[j] = -INFINITY; id[j] = -1; }
         float* ms = merge_s + quarter * SC_KT * 32;
         int* mi = merge_i + quarter * SC_KT * 32;
-        // one candidate list per (query row, piece): merge the two column halves, write, pad the row's unused lists
-        auto flush = [&](int b, bool last_piece) {
+        // one candidate list per (query row, doc range): merge the two column halves, write; range 0 also pads the
+        // row's unused lists
+        auto flush = [&](int b, int r) {
             if (half == 1) {
 #pragma unroll
                 for (int j = 0; j < SC_KT; ++j) { ms[j * 32 + lane] = sc[j]; mi[j * 32 + lane] = id[j]; }
@@ -197,8 +208,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             named_bar_sync(1 + quarter, 64);
             const int row = b * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32 + lane;
             if (half == 0 && row < g.nq) {
-                const int slot = pair - static_cast<int>(static_cast<long long>(b) * g.T / g.chunk);
-                long long base = (static_cast<long long>(row) * g.lists + slot) * SC_KT;
+                long long base = (static_cast<long long>(row) * g.lists + r) * SC_KT;
 #pragma unroll
                 for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
                     *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
@@ -206,9 +216,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     *reinterpret_cast<int4*>(g.cand_ids + base + j4 * 4) =
                         make_int4(id[j4 * 4], id[j4 * 4 + 1], id[j4 * 4 + 2], id[j4 * 4 + 3]);
                 }
-                if (last_piece) {
-                    for (int s2 = slot + 1; s2 < g.lists; ++s2) {
-                        base += SC_KT;
+                if (r == 0) {
+                    base = (static_cast<long long>(row) * g.lists + g.R) * SC_KT;
+                    for (int s2 = g.R; s2 < g.lists; ++s2, base += SC_KT) {
 #pragma unroll
                         for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
                             *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
@@ -223,38 +233,35 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         };
         const uint32_t ltempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
         const uint32_t ltempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
-        int b = static_cast<int>(u0 / g.T), t = static_cast<int>(u0 - static_cast<long long>(b) * g.T);
         int it = 0;
-        for (long long u = u0; u < u1; ++u, ++it) {
-            const int acc = it & 1;
-            mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * SC_BN + half * 128;
-            const long long col_base = static_cast<long long>(t) * SC_BN + half * 128;
+        for (int item = pair; item < g.items; item += num_pairs) {
+            const int t1 = item_t1(item);
+            for (int t = item_t0(item); t < t1; ++t, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * SC_BN + half * 128;
+                const long long col_base = static_cast<long long>(t) * SC_BN + half * 128;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                tmem_ld_wait();
-                if (c == 3) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(acc ? ltempty1 : ltempty0);
-                }
-                const long long c0 = col_base + c * 32;
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(acc ? ltempty1 : ltempty0);
+                    }
+                    const long long c0 = col_base + c * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float s = __uint_as_float(v[j]);
-                    if (s > sc[SC_KT - 1] && c0 + j < g.nd) topk_insert(sc, id, s, static_cast<int>(c0 + j));
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]);
+                        if (s > sc[SC_KT - 1] && c0 + j < g.nd) topk_insert(sc, id, s, static_cast<int>(c0 + j));
+                    }
                 }
             }
-            if (++t == g.T) {  // the query block is finished: this pair holds its last piece
-                flush(b, true);
-                t = 0;
-                ++b;
-            }
+            flush(item_b(item), item / g.QB);
         }
-        if (t != 0) flush(b, false);  // the span ends inside a query block: the next pair continues it
     }
     tc_fence_before();
     cluster_sync_all();  // the peer may still be arriving on this CTA's barriers until here
@@ -277,22 +284,83 @@ __device__ __forceinline__ bool before(float sa, long long ia, float sb, long lo
 }
 
 constexpr int RS_THREADS = 128;
+constexpr int RS_MAX_KEEP = 256;
 
+// One CTA per query. The filter hands over `lists` sorted 16-entry candidate lists (approximate scores). Step 1 (warp 0):
+// multi-way merge of the list heads keeps the `keep` best candidates by approximate score; everything else - docs a list
+// dropped (<= that list's 16th entry) and candidates pruned here (<= the best remaining head) - is bounded by `bound`.
+// Step 2: exact fp32 rescoring of the kept candidates, one warp per candidate. Step 3: top-k by (score desc, id asc)
+// and the proof  bound + eps < k-th exact score  (else the query is flagged for the fp32 scan).
 __global__ void __launch_bounds__(RS_THREADS)
-rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, long long nd, int dim, int lists,
+rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, long long nd, int dim, int lists, int keep,
                     const float* __restrict__ cand_scores, const int* __restrict__ cand_ids,
                     const float* __restrict__ max_doc_norm, int k, long long id_offset, float* __restrict__ out_scores,
                     long long* __restrict__ out_ids, int* __restrict__ flags) {
     extern __shared__ float sm[];
-    const int C = lists * SC_KT;
-    float* qs = sm;               // [dim]
-    float* ex = sm + dim;         // [C] exact scores
+    float* qs = sm;                                   // [dim]
+    float* ex = sm + dim;                             // [keep] exact scores
+    int* sel = reinterpret_cast<int*>(ex + keep);     // [keep] doc ids of the kept candidates (-1 = none)
     __shared__ float red_s[RS_THREADS / 32];
     __shared__ long long red_i[RS_THREADS / 32];
     __shared__ float sh_bound, sh_qnorm;
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* qrow = Q + static_cast<long long>(q) * dim;
+    const float* cs = cand_scores + static_cast<long long>(q) * lists * SC_KT;
+    const int* ci = cand_ids + static_cast<long long>(q) * lists * SC_KT;
+    if (warp == 0) {
+        // lane l owns lists l, l+32, ...: head position per owned list (<= 2 lists per lane for lists <= 64; general loop)
+        float tail = -INFINITY;
+        for (int l = lane; l < lists; l += 32) tail = fmaxf(tail, cs[l * SC_KT + SC_KT - 1]);
+        int head[(SC_MAX_RANGES + 31) / 32 + 1];
+#pragma unroll
+        for (int j = 0; j < (SC_MAX_RANGES + 31) / 32 + 1; ++j) head[j] = 0;
+        for (int m = 0; m < keep; ++m) {
+            // best head of this lane
+            float bs = -INFINITY;
+            int bj = -1;
+#pragma unroll
+            for (int j = 0; j < (SC_MAX_RANGES + 31) / 32 + 1; ++j) {
+                const int l = lane + j * 32;
+                if (l < lists && head[j] < SC_KT) {
+                    const float v = cs[l * SC_KT + head[j]];
+                    if (ci[l * SC_KT + head[j]] >= 0 && (bj < 0 || v > bs)) { bs = v; bj = j; }
+                }
+            }
+            // warp arg-max (ties: lower lane)
+            float ws = bs;
+            int wl = bj >= 0 ? lane : 64;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                if (ol < 64 && (wl >= 64 || os > ws || (os == ws && ol < wl))) { ws = os; wl = ol; }
+            }
+            if (wl >= 64) {  // every list exhausted
+                for (int r = m + lane; r < keep; r += 32) sel[r] = -1;
+                break;
+            }
+            if (lane == wl) {
+#pragma unroll
+                for (int j = 0; j < (SC_MAX_RANGES + 31) / 32 + 1; ++j)
+                    if (j == bj) {
+                        sel[m] = ci[(lane + j * 32) * SC_KT + head[j]];
+                        ++head[j];
+                    }
+            }
+        }
+        // what is left in the lists was pruned: bounded by the best remaining head
+        float rem = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < (SC_MAX_RANGES + 31) / 32 + 1; ++j) {
+            const int l = lane + j * 32;
+            if (l < lists && head[j] < SC_KT && ci[l * SC_KT + head[j]] >= 0) rem = fmaxf(rem, cs[l * SC_KT + head[j]]);
+        }
+        float bnd = fmaxf(tail, rem);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, o));
+        if (lane == 0) sh_bound = bnd;
+    }
     float qq = 0.f;
     for (int i = threadIdx.x; i < dim; i += RS_THREADS) {
         const float v = qrow[i];
@@ -301,17 +369,15 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, lo
     }
     qq = warp_sum_f(qq);
     if (lane == 0) red_s[warp] = qq;
-    __syncthreads();
+    __syncthreads();  // qs, sel, sh_bound, red_s visible
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int i = 0; i < RS_THREADS / 32; ++i) s += red_s[i];
         sh_qnorm = sqrtf(s);
     }
-    const float* cs = cand_scores + static_cast<long long>(q) * C;
-    const int* ci = cand_ids + static_cast<long long>(q) * C;
-    // exact fp32 rescoring: one warp per candidate
-    for (int c = warp; c < C; c += RS_THREADS / 32) {
-        const int id = ci[c];
+    // exact fp32 rescoring: one warp per kept candidate
+    for (int c = warp; c < keep; c += RS_THREADS / 32) {
+        const int id = sel[c];
         float s = -INFINITY;
         if (id >= 0) {
             const float4* drow = reinterpret_cast<const float4*>(D + static_cast<long long>(id) * dim);
@@ -328,20 +394,7 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, lo
         }
         if (lane == 0) ex[c] = s;
     }
-    // bound on everything the filter dropped: max over lists of the list tail (approximate score)
-    float tail = -INFINITY;
-    for (int l = threadIdx.x; l < lists; l += RS_THREADS) tail = fmaxf(tail, cs[l * SC_KT + SC_KT - 1]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tail = fmaxf(tail, __shfl_xor_sync(0xffffffffu, tail, o));
     __syncthreads();  // ex[] complete, red_s reusable
-    if (lane == 0) red_s[warp] = tail;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = red_s[0];
-        for (int i = 1; i < RS_THREADS / 32; ++i) s = fmaxf(s, red_s[i]);
-        sh_bound = s;
-    }
-    __syncthreads();
     // k rounds of block arg-max in (score desc, id asc) order, strictly after the previous winner
     float last_s = INFINITY;
     long long last_i = -1;
@@ -349,8 +402,8 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, lo
     for (int round = 0; round < k; ++round) {
         float bs = -INFINITY;
         long long bi = 0x7fffffffffffffffll;
-        for (int c = threadIdx.x; c < C; c += RS_THREADS) {
-            const int id = ci[c];
+        for (int c = threadIdx.x; c < keep; c += RS_THREADS) {
+            const int id = sel[c];
             if (id < 0) continue;
             const float s = ex[c];
             if (!before(last_s, last_i, s, id)) continue;  // already emitted (or equal to the previous winner)
@@ -373,7 +426,14 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, lo
             out_scores[static_cast<long long>(q) * k + round] = valid ? bs : -INFINITY;
             out_ids[static_cast<long long>(q) * k + round] = valid ? bi + id_offset : -1;
         }
-        if (!valid) { kth = -INFINITY; break; }
+        if (!valid) {
+            for (int r2 = round + 1 + threadIdx.x; r2 < k; r2 += RS_THREADS) {
+                out_scores[static_cast<long long>(q) * k + r2] = -INFINITY;
+                out_ids[static_cast<long long>(q) * k + r2] = -1;
+            }
+            kth = -INFINITY;
+            break;
+        }
         last_s = bs; last_i = bi; kth = bs;
     }
     if (threadIdx.x == 0) {
@@ -394,7 +454,8 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, lo
 // ---------------------------------------------------------------------------------------------
 // Plain fp32 scan: scores[q, doc] = Q[q] . D[doc].  Block = 8 warps; each warp owns docs, up to 8 queries per pass.
 // ---------------------------------------------------------------------------------------------
-constexpr int EX_QB = 8;
+constexpr int EX_QB = 8;   // queries per pass (their rows sit in shared memory)
+constexpr int EX_DW = 4;   // docs per warp per pass: each query float4 read from shared memory feeds 4 doc rows
 
 __global__ void __launch_bounds__(256)
 exact_scores_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ D, long long nd, int dim,
@@ -406,29 +467,43 @@ exact_scores_kernel(const float* __restrict__ Q, int nq, const float* __restrict
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = dim >> 2;
-    for (long long doc = static_cast<long long>(blockIdx.x) * 8 + warp; doc < nd; doc += static_cast<long long>(gridDim.x) * 8) {
-        const float4* drow = reinterpret_cast<const float4*>(D + doc * dim);
-        float acc[EX_QB];
+    const long long groups = (nd + EX_DW - 1) / EX_DW;
+    for (long long gi = static_cast<long long>(blockIdx.x) * 8 + warp; gi < groups; gi += static_cast<long long>(gridDim.x) * 8) {
+        const long long doc0 = gi * EX_DW;
+        const float4* drow[EX_DW];
 #pragma unroll
-        for (int j = 0; j < EX_QB; ++j) acc[j] = 0.f;
+        for (int d = 0; d < EX_DW; ++d) drow[d] = reinterpret_cast<const float4*>(D + min(doc0 + d, nd - 1) * dim);
+        float acc[EX_DW][EX_QB];
+#pragma unroll
+        for (int d = 0; d < EX_DW; ++d)
+#pragma unroll
+            for (int j = 0; j < EX_QB; ++j) acc[d][j] = 0.f;
         for (int i = lane; i < nv; i += 32) {
-            const float4 x = drow[i];
+            float4 x[EX_DW];
+#pragma unroll
+            for (int d = 0; d < EX_DW; ++d) x[d] = __ldcs(drow[d] + i);  // streamed once: do not keep in L1
 #pragma unroll
             for (int j = 0; j < EX_QB; ++j) {
                 if (j < nqb) {
                     const float4 y = reinterpret_cast<const float4*>(qsm + j * dim)[i];
-                    acc[j] = fmaf(x.x, y.x, acc[j]);
-                    acc[j] = fmaf(x.y, y.y, acc[j]);
-                    acc[j] = fmaf(x.z, y.z, acc[j]);
-                    acc[j] = fmaf(x.w, y.w, acc[j]);
+#pragma unroll
+                    for (int d = 0; d < EX_DW; ++d) {
+                        acc[d][j] = fmaf(x[d].x, y.x, acc[d][j]);
+                        acc[d][j] = fmaf(x[d].y, y.y, acc[d][j]);
+                        acc[d][j] = fmaf(x[d].z, y.z, acc[d][j]);
+                        acc[d][j] = fmaf(x[d].w, y.w, acc[d][j]);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < EX_QB; ++j) {
             if (j < nqb) {
-                const float s = warp_sum_f(acc[j]);
-                if (lane == 0) scores[static_cast<long long>(q0 + j) * nd + doc] = s;
+#pragma unroll
+                for (int d = 0; d < EX_DW; ++d) {
+                    const float s = warp_sum_f(acc[d][j]);
+                    if (lane == d && doc0 + d < nd) scores[static_cast<long long>(q0 + j) * nd + doc0 + d] = s;
+                }
             }
         }
     }
@@ -488,6 +563,70 @@ topk_rows_kernel(const float* __restrict__ scores, const long long* __restrict__
     }
 }
 
+// Short rows (cols <= 32*NPL): one WARP per row, the row lives in registers, k rounds of shuffle arg-max - no block barriers.
+// This is the merge of per-rank / per-shard partial top-k lists ([nq, world*k]) and the second pass of the chunked top-k.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+topk_rows_warp_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, int rows, int cols, int k,
+                      long long id_offset, float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* srow = scores + static_cast<long long>(row) * cols;
+    const long long* irow = ids ? ids + static_cast<long long>(row) * cols : nullptr;
+    float s[NPL];
+    long long id[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int c = lane + j * 32;
+        const bool in = c < cols;
+        id[j] = in ? (irow ? irow[c] : static_cast<long long>(c)) : -1;
+        s[j] = (in && id[j] >= 0) ? srow[c] : -INFINITY;
+    }
+    float last_s = INFINITY;
+    long long last_i = -1;
+    for (int round = 0; round < k; ++round) {
+        float bs = -INFINITY;
+        long long bi = 0x7fffffffffffffffll;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            if (id[j] < 0) continue;
+            if (!before(last_s, last_i, s[j], id[j])) continue;
+            if (before(s[j], id[j], bs, bi)) { bs = s[j]; bi = id[j]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (before(os, oi, bs, bi)) { bs = os; bi = oi; }
+        }
+        const bool valid = bi != 0x7fffffffffffffffll;
+        if (lane == 0) {
+            out_scores[static_cast<long long>(row) * k + round] = valid ? bs : -INFINITY;
+            out_ids[static_cast<long long>(row) * k + round] = valid ? bi + id_offset : -1;
+        }
+        if (!valid) {
+            for (int r2 = round + 1 + lane; r2 < k; r2 += 32) {
+                out_scores[static_cast<long long>(row) * k + r2] = -INFINITY;
+                out_ids[static_cast<long long>(row) * k + r2] = -1;
+            }
+            break;
+        }
+        last_s = bs; last_i = bi;
+    }
+}
+
+static int launch_topk_rows(const float* scores, const long long* ids, int rows, long long cols, int k, long long id_offset,
+                            float* out_scores, long long* out_ids, cudaStream_t s) {
+    if (cols <= 128)
+        topk_rows_warp_kernel<4><<<(rows + 7) / 8, 256, 0, s>>>(scores, ids, rows, static_cast<int>(cols), k, id_offset, out_scores, out_ids);
+    else if (cols <= 512)
+        topk_rows_warp_kernel<16><<<(rows + 7) / 8, 256, 0, s>>>(scores, ids, rows, static_cast<int>(cols), k, id_offset, out_scores, out_ids);
+    else
+        topk_rows_kernel<<<rows, 256, 0, s>>>(scores, ids, cols, k, id_offset, cols, out_scores, out_ids);
+    return 0;
+}
+
 // fp32 -> fp16 rows, with the row L2 norms and their maximum (norms are >= 0, so the int view orders them).
 __global__ void f32_to_f16_rows_kernel(const float* __restrict__ src, long long rows, int dim, __half* __restrict__ dst,
                                        float* __restrict__ norms, float* __restrict__ max_norm) {
@@ -543,27 +682,25 @@ static int score_pairs() {
 }
 
 struct ScorePlan {
-    int T, chunk, lists, pairs;
-    long long W;
+    int T, R, QB, items, lists, pairs;
 };
 
 static ScorePlan score_plan(int nq, long long nd) {
-    constexpr int MIN_CHUNK = 4;  // tiles per pair below which the pipeline fill and the extra candidate lists dominate
     ScorePlan p;
-    const int qb = (nq + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    p.QB = (nq + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
     p.T = static_cast<int>((nd + SC_BN - 1) / SC_BN);
-    p.W = static_cast<long long>(qb) * p.T;
     const int P = score_pairs();
-    long long chunk = (p.W + P - 1) / P;
-    if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
-    p.chunk = static_cast<int>(chunk);
-    p.pairs = static_cast<int>((p.W + chunk - 1) / chunk);
-    int pieces = 1;
-    for (int b = 0; b < qb; ++b) {
-        const long long first = static_cast<long long>(b) * p.T / chunk, last = (static_cast<long long>(b + 1) * p.T - 1) / chunk;
-        if (last - first + 1 > pieces) pieces = static_cast<int>(last - first + 1);
+    // time ~ waves * tiles per item, plus a quarter tile per item for the pipeline fill and the list write-out
+    double best = 1e30;
+    p.R = 1;
+    for (int R = 1; R <= SC_MAX_RANGES && R <= p.T; ++R) {
+        const long long waves = (static_cast<long long>(p.QB) * R + P - 1) / P;
+        const double cost = static_cast<double>(waves) * ((p.T + R - 1) / R + 0.25);
+        if (cost < best * 0.98) { best = cost; p.R = R; }  // a larger R must win by 2 %: fewer lists to rescore
     }
-    p.lists = 2 * ((pieces + 1) / 2);
+    p.items = p.QB * p.R;
+    p.pairs = p.items < P ? p.items : P;
+    p.lists = 2 * ((p.R + 1) / 2);
     return p;
 }
 
@@ -605,7 +742,7 @@ extern "C" int vr_score_filter(const void* q_f16, int32_t nq, const void* d_f16,
     if (first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     ScoreArgs g;
-    g.nq = nq; g.nd = nd; g.dim = dim; g.lists = plan.lists; g.T = plan.T; g.chunk = plan.chunk; g.W = plan.W;
+    g.nq = nq; g.nd = nd; g.dim = dim; g.lists = plan.lists; g.T = plan.T; g.R = plan.R; g.QB = plan.QB; g.items = plan.items;
     g.cand_scores = cand_scores; g.cand_ids = cand_ids;
     score_filter_kernel<<<2 * plan.pairs, GEMM_THREADS, Cfg::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, td, g);
     VR_CHECK_CUDA(cudaGetLastError());
@@ -619,13 +756,17 @@ extern "C" int vr_score_rescore(const float* q_f32, int32_t nq, const float* d_f
                "vr_score_rescore: null pointer");
     VR_REQUIRE(nq > 0 && k > 0 && dim % 4 == 0, "vr_score_rescore: bad shape");
     const int lists = ranges * 2;
-    const size_t smem = (static_cast<size_t>(dim) + static_cast<size_t>(lists) * SC_KT) * sizeof(float);
-    VR_REQUIRE(smem <= 200 * 1024, "vr_score_rescore: candidate set too large for shared memory (%zu bytes)", smem);
+    VR_REQUIRE(ranges > 0 && lists <= SC_MAX_RANGES + 1, "vr_score_rescore: ranges must come from vr_score_ranges()");
+    int keep = 2 * k > 32 ? 2 * k : 32;  // candidates rescored per query (the best by approximate score)
+    if (keep > lists * SC_KT) keep = lists * SC_KT;
+    if (keep > RS_MAX_KEEP) keep = RS_MAX_KEEP;
+    const size_t smem = (static_cast<size_t>(dim) + 2 * static_cast<size_t>(keep)) * sizeof(float);
+    VR_REQUIRE(smem <= 200 * 1024, "vr_score_rescore: dim too large for shared memory (%zu bytes)", smem);
     static unsigned long long attr_set = 0;
     if (smem > 48 * 1024 && first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(rescore_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     rescore_topk_kernel<<<nq, RS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        q_f32, d_f32, nd, dim, lists, cand_scores, cand_ids, max_doc_norm, k, id_offset, out_scores,
+        q_f32, d_f32, nd, dim, lists, keep, cand_scores, cand_ids, max_doc_norm, k, id_offset, out_scores,
         reinterpret_cast<long long*>(out_ids), flags);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -640,7 +781,7 @@ extern "C" int vr_score_exact(const float* q_f32, int32_t nq, const float* d_f32
     static unsigned long long attr_set = 0;
     if (smem > 48 * 1024 && first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    long long bx = (nd + 7) / 8;
+    long long bx = (nd + 8 * EX_DW - 1) / (8 * EX_DW);
     const long long cap = static_cast<long long>(num_sms()) * 4;
     if (bx > cap) bx = cap;
     dim3 grid(static_cast<unsigned>(bx), (nq + EX_QB - 1) / EX_QB);
@@ -653,9 +794,8 @@ extern "C" int vr_topk_rows(const float* scores, const int64_t* ids, int32_t row
                             float* out_scores, int64_t* out_ids, void* stream) {
     VR_REQUIRE(scores && out_scores && out_ids, "vr_topk_rows: null pointer");
     VR_REQUIRE(rows > 0 && cols > 0 && k > 0, "vr_topk_rows: bad shape");
-    topk_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        scores, reinterpret_cast<const long long*>(ids), cols, k, id_offset, cols, out_scores,
-        reinterpret_cast<long long*>(out_ids));
+    launch_topk_rows(scores, reinterpret_cast<const long long*>(ids), rows, cols, k, id_offset, out_scores,
+                     reinterpret_cast<long long*>(out_ids), reinterpret_cast<cudaStream_t>(stream));
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -672,9 +812,8 @@ extern "C" int vr_topk_rows_chunked(const float* scores, int32_t rows, int64_t c
                                                         reinterpret_cast<long long*>(ws_ids));
     VR_CHECK_CUDA(cudaGetLastError());
     // pass 2: merge the `chunks` lists of each row (explicit ids; exhausted lists carry id -1 and are skipped)
-    topk_rows_kernel<<<rows, 256, 0, s>>>(ws_scores, reinterpret_cast<const long long*>(ws_ids),
-                                          static_cast<long long>(chunks) * k, k, 0, static_cast<long long>(chunks) * k,
-                                          out_scores, reinterpret_cast<long long*>(out_ids));
+    launch_topk_rows(ws_scores, reinterpret_cast<const long long*>(ws_ids), rows, static_cast<long long>(chunks) * k, k, 0,
+                     out_scores, reinterpret_cast<long long*>(out_ids), s);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -13,6 +13,8 @@ from __future__ import annotations
 
 import functools
 import math
+import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -25,6 +27,16 @@ from .host import PreparedBatch, prepare_batch
 from .weights import sincos_2d
 
 VIT_HEAD_STRIDE = 80  # 72 padded to a multiple of 16 (UMMA K granularity); pad rows of Wqkv are zero
+
+# CUDA-graph path (small batches): eligibility and cache bounds
+GRAPH_MAX_VIT_TOKENS = 32 * 1024   # up to 32 slices of 448x448: beyond that the kernels are long enough to hide launches
+GRAPH_MAX_LM_TOKENS = 4096
+GRAPH_TEXT_BUCKET = 16             # text-only batches: total tokens and longest sequence are padded to multiples of this
+GRAPH_CACHE = 12                   # captured graphs kept (LRU); each owns its activation buffers
+
+
+class _GraphEntry:
+    __slots__ = ("graph", "groups", "src", "pos", "cu", "reps", "launches")
 
 
 def _bf16(t: torch.Tensor, dev) -> torch.Tensor:
@@ -51,7 +63,7 @@ class VisRAGEngine:
     own device current for its launches, so an engine on cuda:1 works while cuda:0 is the process's current device."""
 
     def __init__(self, cfg: VisRAGConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
-                 max_vit_tokens: int = 131072, device_frontend: bool = True):
+                 max_vit_tokens: int = 131072, device_frontend: bool = True, cuda_graphs: Optional[bool] = None):
         cfg.validate()
         L.lib()  # fail loudly if the CUDA library is missing
         self.cfg = cfg
@@ -60,6 +72,12 @@ class VisRAGEngine:
         self.device_frontend = device_frontend
         self.device = L.norm_device(device)
         self.max_vit_tokens = max_vit_tokens
+        # Small batches are launch bound (one query = ~290 ctypes launches of a few microseconds each): their whole
+        # device step is captured into a CUDA graph per shape signature and replayed (see _encode_graphed)
+        self.cuda_graphs = (os.environ.get("VR_CUDA_GRAPHS", "1") != "0") if cuda_graphs is None else bool(cuda_graphs)
+        self._graphs: "OrderedDict[tuple, _GraphEntry]" = OrderedDict()
+        self._graph_seen: Dict[tuple, int] = {}
+        self.graph_stats = {"captured": 0, "replayed": 0, "eager": 0}
         with L.on_device(self.device):
             self._load(cfg, state_dict)
 
@@ -336,6 +354,66 @@ class VisRAGEngine:
         reps = ops.pool_norm(h, self.final_w, self.cfg.rms_eps, cu, pooling, normalize)
         return (reps, h) if return_hidden else reps
 
+    # ------------------------------------------------------------------------------------------ CUDA graphs
+    def _graph_plan(self, pb: PreparedBatch):
+        """Decide whether this batch takes the graph path; text-only batches are padded into shape buckets with ONE extra
+        dummy sequence (token 0, dropped after pooling) so that different queries share a captured graph.
+        Returns (token_src, positions, cu_seqlens, max_len, n_out) or None."""
+        if not self.cuda_graphs or pb.n_items == 0:
+            return None
+        T = int(pb.cu_seqlens[-1])
+        max_len = int(pb.seq_lens.max())
+        vit_tokens = sum(len(v) * (k[0] // self.cfg.patch_size) * (k[1] // self.cfg.patch_size) for k, v in pb.groups.items())
+        if vit_tokens > GRAPH_MAX_VIT_TOKENS or T > GRAPH_MAX_LM_TOKENS:
+            return None
+        if pb.n_slices > 0:
+            return pb.token_src, pb.positions, pb.cu_seqlens, max_len, pb.n_items
+        b = GRAPH_TEXT_BUCKET
+        Tb = -(-(T + 1) // b) * b          # at least one pad token: the dummy sequence is never empty
+        pad = Tb - T
+        Lb = min(-(-max(max_len, pad) // b) * b, self.cfg.max_pos)
+        if pad > self.cfg.max_pos:
+            return None
+        src = np.concatenate([pb.token_src, np.full(pad, -1, dtype=np.int32)])        # -(0 + 1): token id 0
+        pos = np.concatenate([pb.positions, np.arange(pad, dtype=np.int32)])
+        cu = np.concatenate([pb.cu_seqlens, np.asarray([Tb], dtype=np.int32)])
+        return src, pos, cu, Lb, pb.n_items
+
+    def _encode_graphed(self, sig, groups, group_row0, n_slices, src, pos, cu, max_len, pooling, normalize):
+        """Replay (or, on the second sighting of a signature, capture) the device step for this shape. The first sighting
+        runs eagerly: it also warms every per-shape table and one-time kernel attribute the capture must not touch."""
+        ent = self._graphs.get(sig)
+        if ent is None:
+            seen = self._graph_seen.get(sig, 0)
+            self._graph_seen[sig] = seen + 1
+            if seen == 0:
+                self.graph_stats["eager"] += 1
+                return self.encode_device(groups, group_row0, n_slices, src, pos, cu, max_len, pooling, normalize)
+            ent = _GraphEntry()
+            ent.groups = {k: v.clone() for k, v in groups.items()}
+            ent.src, ent.pos, ent.cu = src.clone(), pos.clone(), cu.clone()
+            launches0 = L.LAUNCHES
+            torch.cuda.synchronize(self.device)
+            ent.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ent.graph):
+                ent.reps = self.encode_device(ent.groups, group_row0, n_slices, ent.src, ent.pos, ent.cu, max_len, pooling, normalize)
+            ent.launches = L.LAUNCHES - launches0
+            self._graphs[sig] = ent
+            self.graph_stats["captured"] += 1
+            while len(self._graphs) > GRAPH_CACHE:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(sig)
+            for k, v in groups.items():
+                ent.groups[k].copy_(v, non_blocking=True)
+            ent.src.copy_(src, non_blocking=True)
+            ent.pos.copy_(pos, non_blocking=True)
+            ent.cu.copy_(cu, non_blocking=True)
+        ent.graph.replay()
+        L.LAUNCHES += ent.launches  # the kernels of the captured step launch again (the counter is the bench's claim)
+        self.graph_stats["replayed"] += 1
+        return ent.reps.clone()
+
     @_on_own_device
     def encode_prepared(self, pb: PreparedBatch, pooling: str = "wmean", normalize: bool = True,
                         return_hidden: bool = False):
@@ -343,6 +421,15 @@ class VisRAGEngine:
             return torch.zeros((0, self.cfg.hidden), dtype=torch.float32, device=self.device)
         if int(pb.seq_lens.max()) > self.cfg.max_pos:
             raise ValueError(f"sequence longer than max_pos={self.cfg.max_pos}")
+        plan = None if return_hidden or ops.profiling() else self._graph_plan(pb)
+        if plan is not None:
+            src_h, pos_h, cu_h, max_len, n_out = plan
+            shaped = PreparedBatch(pb.n_items, pb.seq_lens, cu_h, pos_h, src_h, pb.groups, pb.group_row0, pb.n_slices, pb.jobs)
+            groups, src, pos, cu = self.upload(shaped)
+            sig = (tuple(sorted((k, v.shape[0]) for k, v in groups.items())), tuple(sorted(pb.group_row0.items())), pb.n_slices,
+                   int(src.shape[0]), int(cu.shape[0]), max_len, pooling, bool(normalize))
+            reps = self._encode_graphed(sig, groups, pb.group_row0, pb.n_slices, src, pos, cu, max_len, pooling, normalize)
+            return reps[:n_out]
         groups, src, pos, cu = self.upload(pb)
         return self.encode_device(groups, pb.group_row0, pb.n_slices, src, pos, cu, int(pb.seq_lens.max()), pooling,
                                   normalize, return_hidden)

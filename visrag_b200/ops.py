@@ -18,6 +18,11 @@ def profile_begin() -> None:
     _PROF = []
 
 
+def profiling() -> bool:
+    """True while per-launch event profiling is on (the engine then avoids CUDA-graph capture and replay)."""
+    return _PROF is not None
+
+
 def profile_end():
     """Stop recording; returns {kind: (launches, total_ms, total_flops)} (synchronises the device)."""
     global _PROF
