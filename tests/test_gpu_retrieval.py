@@ -280,7 +280,8 @@ def test_filter_candidate_lists_cover_every_query_block_piece(nq, nd, d):
     ci, cs = cand_i.cpu().numpy().reshape(nq, lists, kt), cand_s.cpu().numpy().reshape(nq, lists, kt)
     assert not np.isnan(cs).any() and ((ci == -1) | ((ci >= 0) & (ci < nd))).all()
     assert (cs[:, :, 1:] <= cs[:, :, :-1]).all()                  # every list sorted descending (empties are -inf)
-    assert (np.isinf(cs) == (ci == -1)).all()
+    assert (np.isinf(cs) == (ci == -1))[:, :-1].all()             # (the last slot's first score is the query's threshold)
+    assert (ci[:, -1] == -1).all()
     approx = (q16.float() @ idx.emb_f16.float().T).cpu().numpy()  # fp16 operands, fp32 accumulate like the filter
     for r in rs.choice(nq, 40, replace=False):
         have = set(ci[r][ci[r] >= 0].tolist())

@@ -2,6 +2,7 @@
 encode loop, host PIL front-end vs device front-end. Prints pages/s, slices/s and checks that both give identical
 embeddings.   python tools/bench_mixed.py [--pages 256] [--batch 32]"""
 import argparse
+import json
 import os
 import sys
 import time
@@ -45,8 +46,10 @@ def main():
         data.append({"id": f"p{i}", "text": "", "image": Image.fromarray(rs.randint(0, 256, (h, w, 3), dtype=np.uint8))})
         slices += plan_slices(w, h, cfg).n_slices
     kw = {"tokenizer": tok, "max_inp_length": 2048}
-    print(f"{a.pages} pages, formats {formats}, {slices} slices ({slices / a.pages:.2f} per page), batch {a.batch}", flush=True)
-    res = {}
+    print(f"{a.pages} pages, formats {formats}, {slices} slices ({slices / a.pages:.2f} per page), batch {a.batch}", file=sys.stderr, flush=True)
+    res, line = {}, {"what": "BASELINE configs[4] flavour: mixed-resolution pages through inference.encode_stream, full-size model",
+                     "pages": a.pages, "page_formats_wh": formats, "slices": slices, "slices_per_page": round(slices / a.pages, 2),
+                     "pages_per_batch": a.batch, "slices_per_batch": round(slices / a.pages * a.batch, 1)}
     for name, dev in (("host PIL front-end", False), ("device front-end", True)):
         lm.engine.device_frontend = dev
         for _ in I.encode_stream(I._batches(data[: 2 * a.batch], a.batch), model, kw):
@@ -57,9 +60,12 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         res[name] = out
-        print(f"{name:20s}: {a.pages / dt:7.1f} pages/s  {slices / dt:7.1f} slices/s  ({dt * 1e3:.0f} ms)", flush=True)
+        print(f"{name:20s}: {a.pages / dt:7.1f} pages/s  {slices / dt:7.1f} slices/s  ({dt * 1e3:.0f} ms)", file=sys.stderr, flush=True)
+        line[name] = {"pages_per_s": round(a.pages / dt, 1), "slices_per_s": round(slices / dt, 1), "ms": round(dt * 1e3, 1)}
     same = np.array_equal(res["host PIL front-end"], res["device front-end"])
-    print("embeddings identical:", same)
+    line["embeddings_identical_between_front_ends"] = bool(same)
+    line["graph_stats"] = dict(lm.engine.graph_stats)
+    print(json.dumps(line), flush=True)
     return 0 if same else 1
 
 

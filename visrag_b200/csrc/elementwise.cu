@@ -83,41 +83,55 @@ im2col_norm_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, int pat
 // of 14 bf16 (one per channel) in the patch's output row. Bytes become floats with one PRMT each (0x4B0000xx = 2^23 + u,
 // then - 2^23: exact, and no I2F on the quarter-rate conversion pipe), the output rows of the strip are assembled in
 // shared memory and leave with ONE bulk (TMA) store per strip while the next strip is being loaded.
-constexpr int IM2COL14_THREADS = 256;
+constexpr int IM2COL14_THREADS = 224;  // 7 warps: 14 pixel rows x 16 patches per round
 
 __global__ void __launch_bounds__(IM2COL14_THREADS)
 im2col_norm14_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, __nv_bfloat16* __restrict__ out, int ldo) {
     constexpr int P = 14, RUN = P * 3;  // 42 bytes per (patch, pixel row)
     extern __shared__ __align__(16) uint8_t smem14[];
-    const int w3 = gw * RUN;
-    const int strip_bytes = P * w3;
-    const int in_bytes = (strip_bytes + 8 + 15) & ~15;  // + 8: the last item's 12-word window reads past its 42 bytes
+    const int w3 = gw * RUN;            // bytes per pixel row of the strip (a multiple of 42, hence even)
+    // shared-memory row pitch: 16-byte multiple with an odd number of 16-byte units, so that the 14 pixel rows of a patch
+    // (consecutive lanes) start in different banks (w3 itself is 1344 B = 16 banks apart for 448-pixel slices)
+    const int pitch = (((w3 + 15) >> 4) | 1) << 4;
+    const int in_bytes = P * pitch + 16;  // + 16: the last item's 12-word window reads past its 42 bytes
     uint8_t* strip = smem14;
-    uint8_t* tile = smem14 + in_bytes;  // [gw][ldo] bf16
+    uint8_t* tile = smem14 + in_bytes;    // [gw][ldo] bf16, exactly the layout of the strip's output rows
     const int tile_bytes = gw * ldo * 2;
+    const int strip_bytes = P * w3;
     // zero the padding columns once: they are never written again
     for (int i = threadIdx.x; i < gw * (ldo - 3 * P * P); i += IM2COL14_THREADS) {
         const int p = i / (ldo - 3 * P * P), c = i - p * (ldo - 3 * P * P);
         reinterpret_cast<__nv_bfloat16*>(tile)[p * ldo + 3 * P * P + c] = __float2bfloat16(0.f);
     }
-    for (int i = strip_bytes + threadIdx.x; i < in_bytes; i += IM2COL14_THREADS) strip[i] = 0;
+    for (int i = threadIdx.x; i < in_bytes / 4; i += IM2COL14_THREADS) reinterpret_cast<uint32_t*>(strip)[i] = 0;
+    __syncthreads();
     for (int sidx = blockIdx.x; sidx < n_strips; sidx += gridDim.x) {
         const uint8_t* src = px + static_cast<long long>(sidx) * strip_bytes;
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile free again
-        __syncthreads();
-        if (((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(strip_bytes)) & 15) == 0) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(src);
-            uint4* d4 = reinterpret_cast<uint4*>(strip);
-            for (int i = threadIdx.x; i < (strip_bytes >> 4); i += IM2COL14_THREADS) d4[i] = __ldcs(s4 + i);
-        } else {  // 588*gw bytes at a multiple of that: always 4-byte aligned
-            const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
-            uint32_t* d1 = reinterpret_cast<uint32_t*>(strip);
-            for (int i = threadIdx.x; i < (strip_bytes >> 2); i += IM2COL14_THREADS) d1[i] = __ldcs(s1 + i);
+        // stage the strip row by row (the rows are contiguous in global memory; only the shared-memory pitch differs)
+        if (((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(w3)) & 15) == 0) {
+            const int vpr = w3 >> 4;  // 16-byte vectors per row
+            for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
+                const int r = i / vpr, c = i - r * vpr;
+                *reinterpret_cast<uint4*>(strip + r * pitch + c * 16) = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+            }
+        } else if ((w3 & 3) == 0) {  // 4-byte aligned rows (the strip start always is: 588*gw bytes per strip)
+            const int vpr = w3 >> 2;
+            for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
+                const int r = i / vpr, c = i - r * vpr;
+                *reinterpret_cast<uint32_t*>(strip + r * pitch + c * 4) = __ldcs(reinterpret_cast<const uint32_t*>(src) + i);
+            }
+        } else {  // odd grid width: rows are only 2-byte aligned
+            const int vpr = w3 >> 1;
+            for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
+                const int r = i / vpr, c = i - r * vpr;
+                *reinterpret_cast<unsigned short*>(strip + r * pitch + c * 2) = __ldcs(reinterpret_cast<const unsigned short*>(src) + i);
+            }
         }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous strip's tile has left
         __syncthreads();
         for (int it = threadIdx.x; it < gw * P; it += IM2COL14_THREADS) {
             const int p = it / P, ky = it - p * P;
-            const int off = ky * w3 + p * RUN;  // even
+            const int off = ky * pitch + p * RUN;  // even
             const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(strip + (off & ~3));
             uint32_t w[12];
 #pragma unroll
@@ -305,7 +319,7 @@ constexpr int POOL_WARPS = POOL_THREADS / 32;
 constexpr int POOL_CLUSTER = 8;
 
 template <int VPL, bool EXACT>
-__global__ void __cluster_dims__(POOL_CLUSTER, 1, 1) __launch_bounds__(POOL_THREADS)
+__global__ void __cluster_dims__(POOL_CLUSTER, 1, 1) __launch_bounds__(POOL_THREADS, VPL <= 18 ? 5 : 2)
 pool_norm_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ gamma, float eps,
                  const int* __restrict__ cu, int dim, int pooling, int normalize, float* __restrict__ reps) {
     extern __shared__ __align__(16) float pool_smem[];  // [POOL_WARPS][VPL*128] staging, reused as the CTA's partial vector
@@ -326,16 +340,18 @@ pool_norm_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     int t_lo = 0, t_hi = len;  // rows that carry weight
     if (pooling == 2) t_lo = len - 1;
     if (pooling == 3) t_hi = 1;
-    float4 acc[VPL];
+    // the warp's accumulator lives in its shared-memory staging row (registers hold one input row: ~100 per thread,
+    // five CTAs per SM; with a register accumulator it was 164 and three)
+    float4* stage = reinterpret_cast<float4*>(pool_smem) + warp * (COLS / 4);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < VPL; ++i) stage[lane + i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = t_lo + static_cast<int>(rank) * POOL_WARPS + warp; t < t_hi; t += POOL_CLUSTER * POOL_WARPS) {
         const float4* xr = reinterpret_cast<const float4*>(h + static_cast<long long>(begin + t) * ldh);
         float4 v[VPL];
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const int c = lane + i * 32;
-            v[i] = (EXACT || c < nvec) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = (EXACT || c < nvec) ? __ldcs(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float ss = 0.f;
 #pragma unroll
@@ -345,14 +361,13 @@ pool_norm_kernel(const float* __restrict__ h, long long ldh, const float* __rest
         const float sc = w * rsqrtf(ss / static_cast<float>(dim) + eps);
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            acc[i].x += sc * v[i].x; acc[i].y += sc * v[i].y; acc[i].z += sc * v[i].z; acc[i].w += sc * v[i].w;
+            float4 a = stage[lane + i * 32];
+            a.x += sc * v[i].x; a.y += sc * v[i].y; a.z += sc * v[i].z; a.w += sc * v[i].w;
+            stage[lane + i * 32] = a;
         }
     }
-    float4* stage = reinterpret_cast<float4*>(pool_smem) + warp * (COLS / 4);
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) stage[lane + i * 32] = acc[i];
     __syncthreads();
-    // CTA partial: column-wise sum over the 8 warps, written over warp 0's staging area
+    // CTA partial: column-wise sum over the warps, written over warp 0's staging area
     for (int c = threadIdx.x; c < COLS / 4; c += POOL_THREADS) {
         float4 s4 = reinterpret_cast<const float4*>(pool_smem)[c];
 #pragma unroll
@@ -431,8 +446,9 @@ extern "C" int vr_im2col_norm(const uint8_t* pixels, int32_t n_slices, int32_t h
     VR_REQUIRE(n_strips < (1ll << 31), "vr_im2col_norm: too many patch rows");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     long long blocks = n_strips;
-    if (patch == 14 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(pixels) & 3) == 0) {
-        const size_t smem14 = ((static_cast<size_t>(14) * w * 3 + 8 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(gw) * ldo * 2;
+    if (patch == 14 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(pixels) & 3) == 0 && (ldo & 7) == 0) {
+        const size_t pitch14 = static_cast<size_t>((((w * 3 + 15) >> 4) | 1) << 4);
+        const size_t smem14 = 14 * pitch14 + 16 + static_cast<size_t>(gw) * ldo * 2;
         if (smem14 <= 200 * 1024) {
             static unsigned long long configured14 = 0;
             if (first_use_on_device(&configured14))

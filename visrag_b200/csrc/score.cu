@@ -31,7 +31,8 @@ constexpr int SC_MAX_RANGES = 64;  // doc ranges (= candidate lists per query) t
 // tile is fetched from HBM once and then served to the other query blocks from L2. (A contiguous "stream-K" split of
 // the b-major tile list balances perfectly but de-phases the pairs: measured 23 GB of DRAM reads instead of 0.6 GB
 // and 6.0 ms instead of the ~4 ms this layout takes at 10 k x 125 k.) R is chosen by the host to fill whole waves
-// (score_plan); every item emits ONE 16-entry candidate list per query, so a query has R lists.
+// (score_plan); every item emits ONE 16-entry candidate list per query, so a query has R lists. Items of later waves
+// start from the threshold the finished items of the same query published (tau, see the epilogue).
 struct ScoreArgs {
     int nq;
     long long nd;
@@ -190,51 +191,18 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int j = 0; j < SC_KT; ++j) { sc[j] = -INFINITY; id[j] = -1; }
         float* ms = merge_s + quarter * SC_KT * 32;
         int* mi = merge_i + quarter * SC_KT * 32;
-        // one candidate list per (query row, doc range): merge the two column halves, write; range 0 also pads the
-        // row's unused lists
-        auto flush = [&](int b, int r) {
-            if (half == 1) {
-#pragma unroll
-                for (int j = 0; j < SC_KT; ++j) { ms[j * 32 + lane] = sc[j]; mi[j * 32 + lane] = id[j]; }
-            }
-            named_bar_sync(1 + quarter, 64);
-            if (half == 0) {
-#pragma unroll
-                for (int j = 0; j < SC_KT; ++j) {
-                    const float v = ms[j * 32 + lane];
-                    if (v > sc[SC_KT - 1]) topk_insert(sc, id, v, mi[j * 32 + lane]);
-                }
-            }
-            named_bar_sync(1 + quarter, 64);
-            const int row = b * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32 + lane;
-            if (half == 0 && row < g.nq) {
-                long long base = (static_cast<long long>(row) * g.lists + r) * SC_KT;
-#pragma unroll
-                for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
-                    *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
-                        make_float4(sc[j4 * 4], sc[j4 * 4 + 1], sc[j4 * 4 + 2], sc[j4 * 4 + 3]);
-                    *reinterpret_cast<int4*>(g.cand_ids + base + j4 * 4) =
-                        make_int4(id[j4 * 4], id[j4 * 4 + 1], id[j4 * 4 + 2], id[j4 * 4 + 3]);
-                }
-                if (r == 0) {
-                    base = (static_cast<long long>(row) * g.lists + g.R) * SC_KT;
-                    for (int s2 = g.R; s2 < g.lists; ++s2, base += SC_KT) {
-#pragma unroll
-                        for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
-                            *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
-                                make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                            *reinterpret_cast<int4*>(g.cand_ids + base + j4 * 4) = make_int4(-1, -1, -1, -1);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < SC_KT; ++j) { sc[j] = -INFINITY; id[j] = -1; }
-        };
         const uint32_t ltempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
         const uint32_t ltempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
         int it = 0;
         for (int item = pair; item < g.items; item += num_pairs) {
+            const int b = item_b(item), r = item / g.QB;
+            const int row = b * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32 + lane;
+            // tau: a lower bound on what this query can still use, published by the items of this query that already
+            // finished (the 16th best score of their doc range). Dropping everything <= tau is covered by the proof: the
+            // rescoring kernel's bound is the maximum over all list tails, and tau is one of them.
+            float* tau_ptr = g.cand_scores + (static_cast<long long>(min(row, g.nq - 1)) * g.lists + g.lists - 1) * SC_KT;
+            const float tau = __ldcg(tau_ptr);
+            float thr = tau;  // max(tau, sc[SC_KT-1])
             const int t1 = item_t1(item);
             for (int t = item_t0(item); t < t1; ++t, ++it) {
                 const int acc = it & 1;
@@ -252,15 +220,72 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(acc ? ltempty1 : ltempty0);
                     }
-                    const long long c0 = col_base + c * 32;
+                    // fast path: nothing of the 32 scores beats the threshold (the common case after the first tiles)
+                    float mx = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (s > sc[SC_KT - 1] && c0 + j < g.nd) topk_insert(sc, id, s, static_cast<int>(c0 + j));
+                    for (int j = 2; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                    if (mx > thr) {
+                        // slow path, ONE compact instance of the insertion code (the fully unrolled form - 32 inlined
+                        // insertions per chunk - thrashed the instruction cache: ncu top stall "no_instruction")
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
+                        const long long c0 = col_base + c * 32;
+#pragma unroll 1
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            // v[j] with a run-time j: binary select tree over the register array
+                            uint32_t s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) s16[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) s8[i] = (j & 2) ? s16[2 * i + 1] : s16[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[2 * i + 1] : s8[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) s2[i] = (j & 8) ? s4[2 * i + 1] : s4[2 * i];
+                            const float sv = __uint_as_float((j & 16) ? s2[1] : s2[0]);
+                            if (sv > thr && c0 + j < g.nd) {
+                                topk_insert(sc, id, sv, static_cast<int>(c0 + j));
+                                thr = fmaxf(tau, sc[SC_KT - 1]);
+                            }
+                        }
                     }
                 }
             }
-            flush(item_b(item), item / g.QB);
+            // one candidate list per (query row, doc range): merge the two column halves (top-16 of the union: its tail
+            // bounds everything either half dropped), write it, publish its tail as the query's new tau
+            if (half == 1) {
+#pragma unroll
+                for (int j = 0; j < SC_KT; ++j) { ms[j * 32 + lane] = sc[j]; mi[j * 32 + lane] = id[j]; }
+            }
+            named_bar_sync(1 + quarter, 64);
+            if (half == 0) {
+#pragma unroll 1
+                for (int j = 0; j < SC_KT; ++j) {
+                    const float v2 = ms[j * 32 + lane];
+                    if (v2 > sc[SC_KT - 1]) topk_insert(sc, id, v2, mi[j * 32 + lane]);
+                }
+            }
+            named_bar_sync(1 + quarter, 64);
+            if (half == 0 && row < g.nq) {
+                const long long base = (static_cast<long long>(row) * g.lists + r) * SC_KT;
+#pragma unroll
+                for (int j4 = 0; j4 < SC_KT / 4; ++j4) {
+                    *reinterpret_cast<float4*>(g.cand_scores + base + j4 * 4) =
+                        make_float4(sc[j4 * 4], sc[j4 * 4 + 1], sc[j4 * 4 + 2], sc[j4 * 4 + 3]);
+                    *reinterpret_cast<int4*>(g.cand_ids + base + j4 * 4) =
+                        make_int4(id[j4 * 4], id[j4 * 4 + 1], id[j4 * 4 + 2], id[j4 * 4 + 3]);
+                }
+                const float tail = sc[SC_KT - 1];
+                if (tail > tau) {  // float max through the integer atomics (tail may be negative)
+                    if (tail >= 0.f) atomicMax(reinterpret_cast<int*>(tau_ptr), __float_as_int(tail));
+                    else atomicMin(reinterpret_cast<unsigned int*>(tau_ptr), __float_as_uint(tail));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SC_KT; ++j) { sc[j] = -INFINITY; id[j] = -1; }
         }
     }
     tc_fence_before();
@@ -653,6 +678,19 @@ __global__ void f32_to_f16_rows_kernel(const float* __restrict__ src, long long 
     }
 }
 
+// Before the filter: every list slot beyond the R real ones becomes an empty list (-inf, -1). The LAST slot doubles as
+// the query's running threshold tau (its first score; id -1 keeps the rescoring kernel from reading it as a candidate).
+__global__ void score_init_lists_kernel(float* __restrict__ cand_scores, int* __restrict__ cand_ids, int nq, int lists, int R) {
+    const int per_row = (lists - R) * SC_KT;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(nq) * per_row;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / per_row;
+        const long long o = (row * lists + R) * SC_KT + (i - row * per_row);
+        cand_scores[o] = -INFINITY;
+        cand_ids[o] = -1;
+    }
+}
+
 // Co-resident CTA pairs of the filter kernel on the current device (GPCs with an odd number of usable SMs cannot pair
 // all of them; a persistent kernel must not launch more clusters than fit at once).
 static int score_pairs() {
@@ -700,7 +738,7 @@ static ScorePlan score_plan(int nq, long long nd) {
     }
     p.items = p.QB * p.R;
     p.pairs = p.items < P ? p.items : P;
-    p.lists = 2 * ((p.R + 1) / 2);
+    p.lists = 2 * ((p.R + 2) / 2);  // >= R + 1: the last slot carries the per-query threshold (score_init_lists_kernel)
     return p;
 }
 
@@ -744,7 +782,15 @@ extern "C" int vr_score_filter(const void* q_f16, int32_t nq, const void* d_f16,
     ScoreArgs g;
     g.nq = nq; g.nd = nd; g.dim = dim; g.lists = plan.lists; g.T = plan.T; g.R = plan.R; g.QB = plan.QB; g.items = plan.items;
     g.cand_scores = cand_scores; g.cand_ids = cand_ids;
-    score_filter_kernel<<<2 * plan.pairs, GEMM_THREADS, Cfg::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, td, g);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {
+        const long long n = static_cast<long long>(nq) * (plan.lists - plan.R) * SC_KT;
+        long long blocks = (n + 255) / 256;
+        if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+        score_init_lists_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(cand_scores, cand_ids, nq, plan.lists, plan.R);
+        VR_CHECK_CUDA(cudaGetLastError());
+    }
+    score_filter_kernel<<<2 * plan.pairs, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tq, td, g);
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -756,7 +802,7 @@ extern "C" int vr_score_rescore(const float* q_f32, int32_t nq, const float* d_f
                "vr_score_rescore: null pointer");
     VR_REQUIRE(nq > 0 && k > 0 && dim % 4 == 0, "vr_score_rescore: bad shape");
     const int lists = ranges * 2;
-    VR_REQUIRE(ranges > 0 && lists <= SC_MAX_RANGES + 1, "vr_score_rescore: ranges must come from vr_score_ranges()");
+    VR_REQUIRE(ranges > 0 && lists <= SC_MAX_RANGES + 2, "vr_score_rescore: ranges must come from vr_score_ranges()");
     int keep = 2 * k > 32 ? 2 * k : 32;  // candidates rescored per query (the best by approximate score)
     if (keep > lists * SC_KT) keep = lists * SC_KT;
     if (keep > RS_MAX_KEEP) keep = RS_MAX_KEEP;
