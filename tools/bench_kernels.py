@@ -128,7 +128,9 @@ def main():
     n_cand = int((ci >= 0).sum().item())
     if not a.ncu:
         print(json.dumps({"note": "filter plan", "lists_per_query": lists, "real_candidates_per_query": round(n_cand / nq, 1)}), flush=True)
-    run("rescore_topk", resc, n_cand * d * 4 + nq * d * 4, 0, a, flush)
+    keep = min(32, lists * kt)  # vr_score_rescore rescoring budget for k = 10: the 32 best candidates by approximate score
+    n_resc = int(torch.clamp((ci >= 0).sum(dim=1), max=keep).sum().item())
+    run("rescore_topk", resc, n_resc * d * 4 + nq * d * 4 + nq * lists * kt * 8, 0, a, flush)
     if not a.ncu and (not a.only or "rescore_topk" in a.only):
         print(json.dumps({"note": "rescore result", "flagged": int(flags.sum().item())}), flush=True)
 

@@ -85,17 +85,22 @@ im2col_norm_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, int pat
 // shared memory and leave with ONE bulk (TMA) store per strip while the next strip is being loaded.
 constexpr int IM2COL14_THREADS = 224;  // 7 warps: 14 pixel rows x 16 patches per round
 
+// BULK: the pixel rows are 16-byte multiples at 16-byte aligned addresses -> the strip is staged by 14 bulk (TMA) row
+// copies onto an mbarrier, double buffered: strip i+1 streams in while strip i is converted (the version with ordinary
+// loads was latency bound: ncu long_scoreboard 7.9 with 21 resident warps per SM).
+template <bool BULK>
 __global__ void __launch_bounds__(IM2COL14_THREADS)
 im2col_norm14_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, __nv_bfloat16* __restrict__ out, int ldo) {
     constexpr int P = 14, RUN = P * 3;  // 42 bytes per (patch, pixel row)
+    constexpr int NBUF = BULK ? 2 : 1;
     extern __shared__ __align__(16) uint8_t smem14[];
+    __shared__ __align__(8) uint64_t bars[2];
     const int w3 = gw * RUN;            // bytes per pixel row of the strip (a multiple of 42, hence even)
     // shared-memory row pitch: 16-byte multiple with an odd number of 16-byte units, so that the 14 pixel rows of a patch
     // (consecutive lanes) start in different banks (w3 itself is 1344 B = 16 banks apart for 448-pixel slices)
     const int pitch = (((w3 + 15) >> 4) | 1) << 4;
     const int in_bytes = P * pitch + 16;  // + 16: the last item's 12-word window reads past its 42 bytes
-    uint8_t* strip = smem14;
-    uint8_t* tile = smem14 + in_bytes;    // [gw][ldo] bf16, exactly the layout of the strip's output rows
+    uint8_t* tile = smem14 + NBUF * in_bytes;  // [gw][ldo] bf16, exactly the layout of the strip's output rows
     const int tile_bytes = gw * ldo * 2;
     const int strip_bytes = P * w3;
     // zero the padding columns once: they are never written again
@@ -103,28 +108,41 @@ im2col_norm14_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, __nv_
         const int p = i / (ldo - 3 * P * P), c = i - p * (ldo - 3 * P * P);
         reinterpret_cast<__nv_bfloat16*>(tile)[p * ldo + 3 * P * P + c] = __float2bfloat16(0.f);
     }
-    for (int i = threadIdx.x; i < in_bytes / 4; i += IM2COL14_THREADS) reinterpret_cast<uint32_t*>(strip)[i] = 0;
+    for (int i = threadIdx.x; i < NBUF * in_bytes / 4; i += IM2COL14_THREADS) reinterpret_cast<uint32_t*>(smem14)[i] = 0;
+    if (BULK && threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async_smem();  // the zero fill above must be ordered before the bulk copies into the same buffers
     __syncthreads();
-    for (int sidx = blockIdx.x; sidx < n_strips; sidx += gridDim.x) {
+    auto issue = [&](int sidx, int buf) {  // thread 0 only
         const uint8_t* src = px + static_cast<long long>(sidx) * strip_bytes;
-        // stage the strip row by row (the rows are contiguous in global memory; only the shared-memory pitch differs)
-        if (((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(w3)) & 15) == 0) {
-            const int vpr = w3 >> 4;  // 16-byte vectors per row
-            for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
-                const int r = i / vpr, c = i - r * vpr;
-                *reinterpret_cast<uint4*>(strip + r * pitch + c * 16) = __ldcs(reinterpret_cast<const uint4*>(src) + i);
-            }
-        } else if ((w3 & 3) == 0) {  // 4-byte aligned rows (the strip start always is: 588*gw bytes per strip)
-            const int vpr = w3 >> 2;
-            for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
-                const int r = i / vpr, c = i - r * vpr;
-                *reinterpret_cast<uint32_t*>(strip + r * pitch + c * 4) = __ldcs(reinterpret_cast<const uint32_t*>(src) + i);
-            }
-        } else {  // odd grid width: rows are only 2-byte aligned
-            const int vpr = w3 >> 1;
-            for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
-                const int r = i / vpr, c = i - r * vpr;
-                *reinterpret_cast<unsigned short*>(strip + r * pitch + c * 2) = __ldcs(reinterpret_cast<const unsigned short*>(src) + i);
+        mbar_expect_tx(&bars[buf], static_cast<uint32_t>(strip_bytes));
+        for (int r = 0; r < P; ++r) bulk_load_1d(smem14 + buf * in_bytes + r * pitch, src + r * w3, static_cast<uint32_t>(w3), &bars[buf]);
+    };
+    if (BULK && threadIdx.x == 0 && blockIdx.x < n_strips) issue(blockIdx.x, 0);
+    int k = 0;
+    for (int sidx = blockIdx.x; sidx < n_strips; sidx += gridDim.x, ++k) {
+        uint8_t* strip = smem14 + (BULK ? (k & 1) * in_bytes : 0);
+        if (BULK) {
+            // buffer (k+1)&1 was read by iteration k-1, which every thread left through the barrier below
+            if (threadIdx.x == 0 && sidx + static_cast<int>(gridDim.x) < n_strips) issue(sidx + gridDim.x, (k + 1) & 1);
+            mbar_wait(&bars[k & 1], (k >> 1) & 1);
+        } else {
+            const uint8_t* src = px + static_cast<long long>(sidx) * strip_bytes;
+            if ((w3 & 3) == 0) {  // 4-byte aligned rows (the strip start always is: 588*gw bytes per strip)
+                const int vpr = w3 >> 2;
+                for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
+                    const int r = i / vpr, c = i - r * vpr;
+                    *reinterpret_cast<uint32_t*>(strip + r * pitch + c * 4) = __ldcs(reinterpret_cast<const uint32_t*>(src) + i);
+                }
+            } else {  // odd grid width: rows are only 2-byte aligned
+                const int vpr = w3 >> 1;
+                for (int i = threadIdx.x; i < P * vpr; i += IM2COL14_THREADS) {
+                    const int r = i / vpr, c = i - r * vpr;
+                    *reinterpret_cast<unsigned short*>(strip + r * pitch + c * 2) = __ldcs(reinterpret_cast<const unsigned short*>(src) + i);
+                }
             }
         }
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous strip's tile has left
@@ -152,7 +170,7 @@ im2col_norm14_kernel(const uint8_t* __restrict__ px, int n_strips, int gw, __nv_
                 }
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy engine
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk copy engine
         __syncthreads();
         if (threadIdx.x == 0) {
             __nv_bfloat16* gdst = out + static_cast<long long>(sidx) * gw * ldo;
@@ -306,27 +324,28 @@ __global__ void build_lm_input_kernel(const int* __restrict__ src, int tokens, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Final RMSNorm + pooling + L2 normalise: one thread-block CLUSTER of 8 CTAs per sequence, every row read from HBM once.
-//   phase 1: the cluster's 32 warps take the weighted rows round-robin; a warp holds its row in registers (VPL float4
+// Final RMSNorm + pooling + L2 normalise: one thread-block CLUSTER of 8 (or 4) CTAs per sequence, every row read from HBM once.
+//   phase 1: the cluster's warps take the weighted rows round-robin; a warp holds its row in registers (VPL float4
 //            per lane), computes 1/rms and adds w_t/rms_t * x_t into its private register accumulator;
 //   phase 2: the 4 warps of a CTA are summed through shared memory (fixed order -> deterministic);
-//   phase 3: after a cluster barrier CTA 0 sums the 8 partial vectors over distributed shared memory, applies
+//   phase 3: after a cluster barrier CTA 0 sums the partial vectors over distributed shared memory, applies
 //            gamma / sum(w), reduces the squared norm, normalises and writes the embedding.
 // pooling: 0 = wmean (w_t = t+1), 1 = mean, 2 = lasttoken, 3 = cls (dense_retrieval_model.py:170-218).
 // ---------------------------------------------------------------------------------------------
 constexpr int POOL_THREADS = 128;  // 4 warps x ~164 registers: three CTAs per SM (256 threads left one)
 constexpr int POOL_WARPS = POOL_THREADS / 32;
-constexpr int POOL_CLUSTER = 8;
+constexpr int POOL_MAX_CLUSTER = 8;  // CTAs per sequence: 8, or 4 when that lets every cluster be resident at once
 
 template <int VPL, bool EXACT>
-__global__ void __cluster_dims__(POOL_CLUSTER, 1, 1) __launch_bounds__(POOL_THREADS, VPL <= 18 ? 5 : 2)
+__global__ void __launch_bounds__(POOL_THREADS, VPL <= 18 ? 5 : 2)
 pool_norm_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ gamma, float eps,
                  const int* __restrict__ cu, int dim, int pooling, int normalize, float* __restrict__ reps) {
     extern __shared__ __align__(16) float pool_smem[];  // [POOL_WARPS][VPL*128] staging, reused as the CTA's partial vector
     __shared__ float red[POOL_WARPS];
     __shared__ float total;
     constexpr int COLS = VPL * 128;
-    const int b = blockIdx.x / POOL_CLUSTER;
+    const unsigned csize = cluster_nctarank();  // set by the launcher (cudaLaunchAttributeClusterDimension)
+    const int b = blockIdx.x / csize;
     const unsigned rank = cluster_ctarank();
     const int begin = cu[b], len = cu[b + 1] - begin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -345,7 +364,7 @@ pool_norm_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     float4* stage = reinterpret_cast<float4*>(pool_smem) + warp * (COLS / 4);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) stage[lane + i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = t_lo + static_cast<int>(rank) * POOL_WARPS + warp; t < t_hi; t += POOL_CLUSTER * POOL_WARPS) {
+    for (int t = t_lo + static_cast<int>(rank) * POOL_WARPS + warp; t < t_hi; t += static_cast<int>(csize) * POOL_WARPS) {
         const float4* xr = reinterpret_cast<const float4*>(h + static_cast<long long>(begin + t) * ldh);
         float4 v[VPL];
 #pragma unroll
@@ -390,8 +409,7 @@ pool_norm_kernel(const float* __restrict__ h, long long ldh, const float* __rest
             const int c = threadIdx.x + k * POOL_THREADS;
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < nvec) {
-#pragma unroll
-                for (unsigned r = 0; r < POOL_CLUSTER; ++r) {
+                for (unsigned r = 0; r < csize; ++r) {
                     const float4 o = ld_shared_cluster_f4(mapa_u32(my + c * 16, r));
                     s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
                 }
@@ -448,16 +466,23 @@ extern "C" int vr_im2col_norm(const uint8_t* pixels, int32_t n_slices, int32_t h
     long long blocks = n_strips;
     if (patch == 14 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(pixels) & 3) == 0 && (ldo & 7) == 0) {
         const size_t pitch14 = static_cast<size_t>((((w * 3 + 15) >> 4) | 1) << 4);
-        const size_t smem14 = 14 * pitch14 + 16 + static_cast<size_t>(gw) * ldo * 2;
+        const bool bulk = ((w * 3) & 15) == 0 && (reinterpret_cast<uintptr_t>(pixels) & 15) == 0;
+        const size_t smem14 = (bulk ? 2 : 1) * (14 * pitch14 + 16) + static_cast<size_t>(gw) * ldo * 2;
         if (smem14 <= 200 * 1024) {
             static unsigned long long configured14 = 0;
-            if (first_use_on_device(&configured14))
-                VR_CHECK_CUDA(cudaFuncSetAttribute(im2col_norm14_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (first_use_on_device(&configured14)) {
+                VR_CHECK_CUDA(cudaFuncSetAttribute(im2col_norm14_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                VR_CHECK_CUDA(cudaFuncSetAttribute(im2col_norm14_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            }
             const long long per_sm = (200 * 1024) / static_cast<long long>(smem14) < 4 ? (200 * 1024) / static_cast<long long>(smem14) : 4;
             const long long cap14 = static_cast<long long>(num_sms()) * (per_sm < 1 ? 1 : per_sm);
             if (blocks > cap14) blocks = cap14;
-            im2col_norm14_kernel<<<static_cast<int>(blocks), IM2COL14_THREADS, smem14, st>>>(
-                pixels, static_cast<int>(n_strips), gw, reinterpret_cast<__nv_bfloat16*>(out), static_cast<int>(ldo));
+            if (bulk)
+                im2col_norm14_kernel<true><<<static_cast<int>(blocks), IM2COL14_THREADS, smem14, st>>>(
+                    pixels, static_cast<int>(n_strips), gw, reinterpret_cast<__nv_bfloat16*>(out), static_cast<int>(ldo));
+            else
+                im2col_norm14_kernel<false><<<static_cast<int>(blocks), IM2COL14_THREADS, smem14, st>>>(
+                    pixels, static_cast<int>(n_strips), gw, reinterpret_cast<__nv_bfloat16*>(out), static_cast<int>(ldo));
             VR_CHECK_CUDA(cudaGetLastError());
             return 0;
         }
@@ -531,14 +556,27 @@ extern "C" int vr_pool_norm(const float* h, int64_t ldh, const float* gamma, flo
                    (reinterpret_cast<uintptr_t>(gamma) & 15) == 0,
                "vr_pool_norm: h, gamma and reps must be 16-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const unsigned grid = static_cast<unsigned>(batch) * POOL_CLUSTER;
+    // 8 CTAs per sequence while all clusters fit on the GPU at once (5 CTAs per SM), else 4: one wave of longer CTAs beats
+    // a second wave of whole clusters (the kernel is a latency chain: load rows -> CTA sum -> cluster sum -> normalise)
+    const unsigned csize = static_cast<long long>(batch) * POOL_MAX_CLUSTER <= static_cast<long long>(num_sms()) * 5 ? POOL_MAX_CLUSTER : 4;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(batch) * csize);
+    cfg.blockDim = dim3(POOL_THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
 #define VR_POOL_LAUNCH(VPL, EXACT)                                                                                        \
     do {                                                                                                                  \
         const int smem = POOL_WARPS * (VPL) * 128 * static_cast<int>(sizeof(float));                                      \
         static unsigned long long configured = 0;                                                                         \
         if (first_use_on_device(&configured))                                                                             \
             VR_CHECK_CUDA(cudaFuncSetAttribute(pool_norm_kernel<VPL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        pool_norm_kernel<VPL, EXACT><<<grid, POOL_THREADS, smem, s>>>(h, ldh, gamma, eps, cu, dim, pooling, normalize, reps); \
+        cfg.dynamicSmemBytes = smem;                                                                                      \
+        VR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pool_norm_kernel<VPL, EXACT>, h, static_cast<long long>(ldh), gamma, eps, cu, dim, \
+                                         pooling, normalize, reps));                                                      \
     } while (0)
     if (dim == 2304) VR_POOL_LAUNCH(18, true);
     else if (dim <= 512) VR_POOL_LAUNCH(4, false);

@@ -482,12 +482,13 @@ rescore_topk_kernel(const float* __restrict__ Q, const float* __restrict__ D, lo
 constexpr int EX_QB = 8;   // queries per pass (their rows sit in shared memory)
 constexpr int EX_DW = 4;   // docs per warp per pass: each query float4 read from shared memory feeds 4 doc rows
 
+template <int NQ>  // queries per pass this instantiation is compiled for (1, 2, 4 or EX_QB): fewer accumulators, deeper unroll
 __global__ void __launch_bounds__(256)
 exact_scores_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ D, long long nd, int dim,
                     float* __restrict__ scores) {
-    extern __shared__ float qsm[];  // [EX_QB, dim]
-    const int q0 = blockIdx.y * EX_QB;
-    const int nqb = min(EX_QB, nq - q0);
+    extern __shared__ float qsm[];  // [NQ, dim]
+    const int q0 = blockIdx.y * NQ;
+    const int nqb = min(NQ, nq - q0);
     for (int i = threadIdx.x; i < nqb * dim; i += blockDim.x) qsm[i] = Q[static_cast<long long>(q0) * dim + i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -498,17 +499,18 @@ exact_scores_kernel(const float* __restrict__ Q, int nq, const float* __restrict
         const float4* drow[EX_DW];
 #pragma unroll
         for (int d = 0; d < EX_DW; ++d) drow[d] = reinterpret_cast<const float4*>(D + min(doc0 + d, nd - 1) * dim);
-        float acc[EX_DW][EX_QB];
+        float acc[EX_DW][NQ];
 #pragma unroll
         for (int d = 0; d < EX_DW; ++d)
 #pragma unroll
-            for (int j = 0; j < EX_QB; ++j) acc[d][j] = 0.f;
+            for (int j = 0; j < NQ; ++j) acc[d][j] = 0.f;
+#pragma unroll(NQ <= 2 ? 3 : 1)
         for (int i = lane; i < nv; i += 32) {
             float4 x[EX_DW];
 #pragma unroll
             for (int d = 0; d < EX_DW; ++d) x[d] = __ldcs(drow[d] + i);  // streamed once: do not keep in L1
 #pragma unroll
-            for (int j = 0; j < EX_QB; ++j) {
+            for (int j = 0; j < NQ; ++j) {
                 if (j < nqb) {
                     const float4 y = reinterpret_cast<const float4*>(qsm + j * dim)[i];
 #pragma unroll
@@ -522,7 +524,7 @@ exact_scores_kernel(const float* __restrict__ Q, int nq, const float* __restrict
             }
         }
 #pragma unroll
-        for (int j = 0; j < EX_QB; ++j) {
+        for (int j = 0; j < NQ; ++j) {
             if (j < nqb) {
 #pragma unroll
                 for (int d = 0; d < EX_DW; ++d) {
@@ -655,19 +657,32 @@ static int launch_topk_rows(const float* scores, const long long* ids, int rows,
 // fp32 -> fp16 rows, with the row L2 norms and their maximum (norms are >= 0, so the int view orders them).
 __global__ void f32_to_f16_rows_kernel(const float* __restrict__ src, long long rows, int dim, __half* __restrict__ dst,
                                        float* __restrict__ norms, float* __restrict__ max_norm) {
+    constexpr int CH = 6;  // float4 per lane in flight (dim 2304 = 3 chunks of 6 x 32 float4)
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const int nv = dim >> 2;
     for (long long r = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); r < rows;
          r += static_cast<long long>(gridDim.x) * warps) {
         const float4* s4 = reinterpret_cast<const float4*>(src + r * dim);
         uint2* d2 = reinterpret_cast<uint2*>(dst + r * dim);
         float ss = 0.f;
-        for (int i = lane; i < (dim >> 2); i += 32) {
-            const float4 v = s4[i];
-            ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-            uint2 pk;
-            pk.x = pack_f16x2(v.x, v.y);
-            pk.y = pack_f16x2(v.z, v.w);
-            d2[i] = pk;
+        for (int i0 = 0; i0 < nv; i0 += CH * 32) {
+            float4 v[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int i = i0 + j * 32 + lane;
+                v[j] = i < nv ? __ldcs(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int i = i0 + j * 32 + lane;
+                ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+                if (i < nv) {
+                    uint2 pk;
+                    pk.x = pack_f16x2(v[j].x, v[j].y);
+                    pk.y = pack_f16x2(v[j].z, v[j].w);
+                    d2[i] = pk;
+                }
+            }
         }
         ss = warp_sum_f(ss);
         if (lane == 0) {
@@ -822,16 +837,26 @@ extern "C" int vr_score_exact(const float* q_f32, int32_t nq, const float* d_f32
                               void* stream) {
     VR_REQUIRE(q_f32 && d_f32 && scores, "vr_score_exact: null pointer");
     VR_REQUIRE(nq > 0 && nd > 0 && dim % 4 == 0, "vr_score_exact: bad shape");
-    const size_t smem = static_cast<size_t>(EX_QB) * dim * sizeof(float);
+    const int NQ = nq >= EX_QB ? EX_QB : (nq >= 4 ? 4 : (nq >= 2 ? 2 : 1));
+    const size_t smem = static_cast<size_t>(NQ) * dim * sizeof(float);
     VR_REQUIRE(smem <= 200 * 1024, "vr_score_exact: dim too large");
-    static unsigned long long attr_set = 0;
-    if (smem > 48 * 1024 && first_use_on_device(&attr_set))
-        VR_CHECK_CUDA(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     long long bx = (nd + 8 * EX_DW - 1) / (8 * EX_DW);
-    const long long cap = static_cast<long long>(num_sms()) * 4;
+    const long long cap = static_cast<long long>(num_sms()) * 3;
     if (bx > cap) bx = cap;
-    dim3 grid(static_cast<unsigned>(bx), (nq + EX_QB - 1) / EX_QB);
-    exact_scores_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q_f32, nq, d_f32, nd, dim, scores);
+    dim3 grid(static_cast<unsigned>(bx), (nq + NQ - 1) / NQ);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define VR_EXACT_LAUNCH(N)                                                                                               \
+    do {                                                                                                                 \
+        static unsigned long long attr_set = 0;                                                                          \
+        if (smem > 48 * 1024 && first_use_on_device(&attr_set))                                                          \
+            VR_CHECK_CUDA(cudaFuncSetAttribute(exact_scores_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        exact_scores_kernel<N><<<grid, 256, smem, st>>>(q_f32, nq, d_f32, nd, dim, scores);                              \
+    } while (0)
+    if (NQ == EX_QB) VR_EXACT_LAUNCH(EX_QB);
+    else if (NQ == 4) VR_EXACT_LAUNCH(4);
+    else if (NQ == 2) VR_EXACT_LAUNCH(2);
+    else VR_EXACT_LAUNCH(1);
+#undef VR_EXACT_LAUNCH
     VR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
