@@ -27,13 +27,13 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
     return 0;
 }
 
-template <int MODE, bool OUT_F32, bool GELU>
+template <int MODE, bool OUT_F32, bool GELU, int BN = 256>
 static int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t stream) {
-    using Cfg = Gemm2Cfg;
+    using Cfg = Gemm2CfgT<BN>;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_2d(&ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, true)) return rc;
-    if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, true)) return rc;
-    auto kern = gemm2_tcgen05_kernel<MODE, OUT_F32, GELU>;
+    if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, BN / 2, GEMM_BK, 128, true)) return rc;
+    auto kern = gemm2_tcgen05_kernel<MODE, OUT_F32, GELU, BN>;
     static unsigned long long attr_set = 0;
     if (first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -67,9 +67,22 @@ static int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, 
     return 0;
 }
 
-// CTA-pair kernel (block_n == 2)
-static int dispatch_mode2(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s) {
+// CTA-pair kernel (block_n == 2: tile width chosen here; block_n == 4: 192-wide tiles forced)
+static int dispatch_mode2(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s, bool force192,
+                          bool allow_narrow) {
     const vr_gemm_epilogue& e = g.epi;
+    // 192-wide tiles where they tile N exactly and 256-wide ones do not (N = 1152: proj, fc2, patch embed)
+    const bool narrow = force192 || (allow_narrow && e.mode == VR_EPI_LINEAR && g.N % 192 == 0 && g.N % 256 != 0);
+    if (narrow) {
+        VR_REQUIRE(e.mode == VR_EPI_LINEAR, "vr_gemm: 192-wide pair tiles (block_n=4) support LINEAR epilogues only");
+        if (e.out_dtype == VR_F32) {
+            VR_REQUIRE(!e.act_gelu, "vr_gemm: GELU epilogue writes bf16 only");
+            return launch_gemm2<VR_EPI_LINEAR, true, false, 192>(A, lda, B, ldb, g, s);
+        }
+        VR_REQUIRE(e.out_dtype == VR_BF16, "vr_gemm: out_dtype must be VR_BF16 or VR_F32");
+        if (e.act_gelu) return launch_gemm2<VR_EPI_LINEAR, false, true, 192>(A, lda, B, ldb, g, s);
+        return launch_gemm2<VR_EPI_LINEAR, false, false, 192>(A, lda, B, ldb, g, s);
+    }
     switch (e.mode) {
         case VR_EPI_LINEAR:
             if (e.out_dtype == VR_F32) {
@@ -163,11 +176,19 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
         // 1585 vs 1334 TFLOP/s, fc2+resid 1290 vs 1094, LM down 1197 vs 1048). Small problems keep 128-row tiles.
         bn = (M > 128 && N >= 256) ? 2 : (N >= 256 ? 256 : 128);
     }
-    if (bn == 2) return dispatch_mode2(A, lda, B, ldb, g, s);
+    if (bn == 2 || bn == 4) {
+        const bool force192 = bn == 4;
+        static int narrow_ok = -1;  // VR_GEMM_NARROW=0 keeps 256-wide tiles everywhere (A/B switch for measurements)
+        if (narrow_ok < 0) {
+            const char* e2 = getenv("VR_GEMM_NARROW");
+            narrow_ok = e2 ? atoi(e2) : 1;
+        }
+        return dispatch_mode2(A, lda, B, ldb, g, s, force192, narrow_ok != 0);
+    }
     if (bn == 3) return dispatch_swapped(A, lda, B, ldb, g, s);
     if (bn == 256) return dispatch_mode<256>(A, lda, B, ldb, g, s);
     if (bn == 128) return dispatch_mode<128>(A, lda, B, ldb, g, s);
-    set_error("vr_gemm: block_n must be 0 (auto), 128, 256, 2 (CTA-pair kernel) or 3 (feature-major accumulator)");
+    set_error("vr_gemm: block_n must be 0 (auto), 128, 256, 2 (CTA-pair kernel), 4 (CTA pair, 192-wide tiles) or 3 (feature-major accumulator)");
     return 2;
 }
 

@@ -12,22 +12,27 @@
 
 namespace vr {
 
-struct Gemm2Cfg {
-    static constexpr int BN = 256;
+// BN_ = 256, or 192 for N = 1152 (proj, fc2: 1152 = 6 x 192 tiles exactly, where 256-wide tiles compute 4.5 -> 5 tiles, 10 %
+// of the MMAs on zero padding). 192-wide tiles support the LINEAR epilogues only (RoPE / SwiGLU work on 64-column pairs).
+template <int BN_>
+struct Gemm2CfgT {
+    static constexpr int BN = BN_;
     static constexpr int STAGES = 6;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;      // this CTA's 128 rows
-    static constexpr int B_BYTES = 128 * GEMM_BK * 2;          // this CTA's half of the 256 N rows
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB
+    static constexpr int B_BYTES = (BN_ / 2) * GEMM_BK * 2;    // this CTA's half of the BN N rows
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB (28 KB for BN = 192)
     static constexpr int EPI_STAGE_BYTES = 4096;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 512;
 };
+using Gemm2Cfg = Gemm2CfgT<256>;
 
-template <int MODE, bool OUT_F32, bool GELU>
+template <int MODE, bool OUT_F32, bool GELU, int BN_ = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmArgs g) {
-    using Cfg = Gemm2Cfg;
+    using Cfg = Gemm2CfgT<BN_>;
+    static_assert(BN_ == 256 || (BN_ == 192 && MODE == VR_EPI_LINEAR), "192-wide tiles: LINEAR epilogues only");
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BN = Cfg::BN;
 
@@ -85,7 +90,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             uint32_t phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
                 const int m0 = (t / tiles_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
-                const int n0 = (t % tiles_n) * BN + static_cast<int>(rank) * 128;
+                const int n0 = (t % tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
