@@ -71,8 +71,11 @@ static int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, 
 static int dispatch_mode2(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s, bool force192,
                           bool allow_narrow) {
     const vr_gemm_epilogue& e = g.epi;
-    // 192-wide tiles where they tile N exactly and 256-wide ones do not (N = 1152: proj, fc2, patch embed)
-    const bool narrow = force192 || (allow_narrow && e.mode == VR_EPI_LINEAR && g.N % 192 == 0 && g.N % 256 != 0);
+    // 192-wide tiles where they tile N exactly and 256-wide ones do not (N = 1152), for SHORT main loops only. Measured in
+    // the bench step (1.42-1.45 GHz): proj (K = 1152) 791 -> 860 TFLOP/s, patch embed (K = 640) 419 -> 460, but fc2
+    // (K = 4304) 1246 -> 1174: an MMA costs a fixed ~34 cycles plus N/2, so with a long K loop the wider tile's better
+    // per-column rate outweighs the 10 % of zero padding it computes.
+    const bool narrow = force192 || (allow_narrow && e.mode == VR_EPI_LINEAR && g.N % 192 == 0 && g.N % 256 != 0 && g.K <= 2304);
     if (narrow) {
         VR_REQUIRE(e.mode == VR_EPI_LINEAR, "vr_gemm: 192-wide pair tiles (block_n=4) support LINEAR epilogues only");
         if (e.out_dtype == VR_F32) {
