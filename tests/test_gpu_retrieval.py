@@ -171,7 +171,7 @@ def _nccl_worker(rank, world, port, out_q):
     try:
         dev = f"cuda:{rank}"
         g = torch.Generator(device=dev).manual_seed(1234)           # same stream on every rank: the FULL corpus / query set
-        D = torch.nn.functional.normalize(torch.randn(6000, 256, device=dev, generator=g), dim=1)
+        D = torch.nn.functional.normalize(torch.randn(12000, 256, device=dev, generator=g), dim=1)  # 6000 per shard: filter path
         Q = torch.nn.functional.normalize(torch.randn(1000, 256, device=dev, generator=g), dim=1)
         lo, hi = R.shard_range(D.shape[0], rank, world)
         index = R.build_index(D[lo:hi].contiguous())
