@@ -69,11 +69,12 @@ int vr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_d
             const vr_gemm_epilogue* epi, void* stream);
 
 /* Same operation with the kernel variant chosen by the caller (benchmarks, parity tests of every variant):
- *   block_n = 0    what vr_gemm picks: the CTA-pair kernel when M > 128 and N >= 256, else 128-row tiles
+ *   block_n = 0    what vr_gemm picks: the CTA-pair kernel when M > 128 and N >= 256, 128 x 64 tiles when M <= 128
+ *                  (weight-streaming bound: more, narrower tiles), else 128-row tiles
  *   block_n = 2    CTA-pair kernel (tcgen05 cta_group::2, one 256x256 tile per pair of SMs, each CTA stages half of B);
  *                  LINEAR epilogues with N % 192 == 0, N % 256 != 0 and K <= 2304 (proj: N = K = 1152) use 256x192 tiles
  *   block_n = 4    CTA-pair kernel with 256x192 tiles forced (LINEAR epilogues only)
- *   block_n = 256 / 128   single-CTA kernel, token-major accumulator, 128 tokens x block_n features per tile
+ *   block_n = 256 / 128 / 64   single-CTA kernel, token-major accumulator, 128 tokens x block_n features per tile
  *   block_n = 3    single-CTA kernel, feature-major accumulator (the weight tile is the MMA's M operand), LINEAR
  *                  epilogues only; its epilogue needs no shared-memory transpose */
 int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_dtype, int32_t M, int32_t N,

@@ -14,7 +14,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
     // both operands use 128-row x 64-column boxes, so the maps are interchangeable: SWAP hands the weight to the MMA's
     // M side (128 features per tile) and the activations to its N side (BN tokens per tile)
     if (int rc = make_tmap_2d(SWAP ? &tb : &ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, bf16)) return rc;
-    if (int rc = make_tmap_2d(SWAP ? &ta : &tb, B, g.N, g.K, ldb, 128, GEMM_BK, 128, bf16)) return rc;
+    if (int rc = make_tmap_2d(SWAP ? &ta : &tb, B, g.N, g.K, ldb, BN < 128 ? BN : 128, GEMM_BK, 128, bf16)) return rc;
     auto kern = gemm_tcgen05_kernel<BN, MODE, OUT_F32, GELU, AB_FMT, SWAP>;
     static unsigned long long attr_set = 0;  // per template instantiation, one bit per device
     if (first_use_on_device(&attr_set))
@@ -177,7 +177,9 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
         // CTA-pair kernel (tcgen05 cta_group::2) wherever a pair has a full 256-row tile to work on: each SM stages only
         // half of B, which lifts the shared-memory/L2 feed limit of the single-CTA kernel (measured, in isolation: qkv
         // 1585 vs 1334 TFLOP/s, fc2+resid 1290 vs 1094, LM down 1197 vs 1048). Small problems keep 128-row tiles.
-        bn = (M > 128 && N >= 256) ? 2 : (N >= 256 ? 256 : 128);
+        // M <= 128 (a few queries): one row tile, the kernel only streams the weight - 64-wide feature tiles spread that
+        // stream over 4x as many SMs as 256-wide ones (o_proj 2304x2304: 36 CTAs instead of 9)
+        bn = (M > 128 && N >= 256) ? 2 : (M <= 128 ? 64 : (N >= 256 ? 256 : 128));
     }
     if (bn == 2 || bn == 4) {
         const bool force192 = bn == 4;
@@ -191,7 +193,8 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
     if (bn == 3) return dispatch_swapped(A, lda, B, ldb, g, s);
     if (bn == 256) return dispatch_mode<256>(A, lda, B, ldb, g, s);
     if (bn == 128) return dispatch_mode<128>(A, lda, B, ldb, g, s);
-    set_error("vr_gemm: block_n must be 0 (auto), 128, 256, 2 (CTA-pair kernel), 4 (CTA pair, 192-wide tiles) or 3 (feature-major accumulator)");
+    if (bn == 64) return dispatch_mode<64>(A, lda, B, ldb, g, s);
+    set_error("vr_gemm: block_n must be 0 (auto), 64, 128, 256, 2 (CTA-pair kernel), 4 (CTA pair, 192-wide tiles) or 3 (feature-major accumulator)");
     return 2;
 }
 

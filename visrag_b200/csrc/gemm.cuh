@@ -25,13 +25,13 @@ constexpr int GEMM_THREADS = (4 + GEMM_EPI_WARPS) * 32;
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 64 ? 7 : 6);
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
+    static constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: power of two >= 32
 };
 
 struct GemmArgs {
@@ -548,7 +548,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int ew = warp - 4;
         const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
         const int half = ew >> 2;              // which half of the BN columns
-        constexpr int COLS_PER_WARP = BN / 2;  // 128 or 64
+        constexpr int COLS_PER_WARP = BN / 2;  // 128, 64 or 32
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -579,6 +579,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     if (SWAP) epi_linear_t<OUT_F32, GELU>(g, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);
                     else epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v, bias4, c);
+                }
+            } else if (BN == 64) {
+                // one 64-column block (a RoPE head / a gate|up pair) per tile: the half-0 warps take it, the others only
+                // hand the accumulator stage back
+                if (half == 0) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32(taddr, r0);
+                    tmem_ld_32x32(taddr + 32, r1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    float a[32], b[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        a[j] = __uint_as_float(r0[j]);
+                        b[j] = __uint_as_float(r1[j]);
+                    }
+                    if (n0 < g.N) {
+                        if (MODE == VR_EPI_ROPE) epi_rope(g, st, lane, row0, n0, a, b);
+                        else epi_swiglu(g, st, lane, row0, n0, a, b);
+                    }
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
             } else {
 #pragma unroll 1
