@@ -470,7 +470,9 @@ def run_ours(a):
             "roofline": roofline, "kernel_time_share": shares,
             "model_tflops": round(total_flops_per_page(n_patches, lm_tokens) * value / 1e12 / world, 1) if n_patches else None,
             "queries": {"queries_per_s_encode_plus_top10": round(nq / (q_ms / 1e3), 1), "retrieve_only_queries_per_s": round(nq / (r_ms / 1e3), 1),
-                        "n_queries": nq, "corpus_pages": nd * world, "k": 10, "query_encode": f"sharded by rank ({qhi - qlo} of {nq} on rank 0)",
+                        "n_queries": nq, "corpus_pages": nd * world, "k": 10,
+                        "lm_tokens_per_query": round(sum(len(tok.encode(t)) for t in qtexts[:64]) / max(1, len(qtexts[:64])), 1),
+                        "tokenizer": "character-level stub (no SentencePiece model ships with the reference): ~4x the tokens a real one gives", "query_encode": f"sharded by rank ({qhi - qlo} of {nq} on rank 0)",
                         "collectives": (["all_gather_into_tensor of [ceil(nq/world), 2304] fp32 query embeddings",
                                          "all_gather_into_tensor of [nq, 10] (score, id) pairs"] if world > 1 else []),
                         "checked_vs_torch_fp32_under_nccl": checked},
