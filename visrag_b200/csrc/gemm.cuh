@@ -34,19 +34,6 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: power of two >= 32
 };
 
-// First k-block of the main loop for the output columns starting at n0 (see the TMA producers). VR_GEMM_KROT=0 at build
-// time keeps the natural order.
-#ifndef VR_GEMM_KROT
-#define VR_GEMM_KROT 1
-#endif
-__device__ __forceinline__ int gemm_k_rotation(int n0, int num_kb) {
-#if VR_GEMM_KROT
-    return static_cast<int>((static_cast<unsigned>(n0 >> 8) * 5u) % static_cast<unsigned>(num_kb));
-#else
-    return 0;
-#endif
-}
-
 struct GemmArgs {
     int M, N, K;
     int prefetch_resid;  // 1: warp 3 pulls the fp32 residual tile into L2 ahead of the epilogue (set by the launcher)
@@ -477,24 +464,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const int m0 = tile_m0(t);
                 const int n0 = tile_n0(t);
-                // K order rotated per 256-column block of the output (gemm_k_rotation): tiles that run at the same time on
-                // different SMs then ask L2 for DIFFERENT k-blocks of the activation rows they share instead of all for the
-                // same 16 KB. Every kernel variant uses the same rotation for the same output columns, so the fp32
-                // accumulation order of an output element does not depend on which variant (i.e. which batch size) ran.
-                int kx = SWAP ? 0 : gemm_k_rotation(n0, num_kb);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::A_BYTES, kx * GEMM_BK, m0);
+                    tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::A_BYTES, kb * GEMM_BK, m0);
                     if (BN == 256) {
                         // a TMA box is at most 256 rows; keep boxes at 128 rows for both operands
-                        tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::B_BYTES, kx * GEMM_BK, n0);
+                        tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::B_BYTES, kb * GEMM_BK, n0);
                         tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::B_BYTES + Cfg::B_BYTES / 2,
-                                    kx * GEMM_BK, n0 + 128);
+                                    kb * GEMM_BK, n0 + 128);
                     } else {
-                        tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::B_BYTES, kx * GEMM_BK, n0);
+                        tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::B_BYTES, kb * GEMM_BK, n0);
                     }
-                    if (++kx == num_kb) kx = 0;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }

@@ -91,14 +91,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
                 const int m0 = (t / tiles_n) * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
                 const int n0 = (t % tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
-                int kx = gemm_k_rotation((t % tiles_n) * BN, num_kb);  // same rotation as the single-CTA kernels (gemm.cuh)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     const uint32_t lfull = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     mbar_expect_tx_cluster(lfull, Cfg::STAGE_BYTES);
-                    tma_load_2d_2sm(&tmap_a, lfull, smem_a + stage * Cfg::A_BYTES, kx * GEMM_BK, m0);
-                    tma_load_2d_2sm(&tmap_b, lfull, smem_b + stage * Cfg::B_BYTES, kx * GEMM_BK, n0);
-                    if (++kx == num_kb) kx = 0;
+                    tma_load_2d_2sm(&tmap_a, lfull, smem_a + stage * Cfg::A_BYTES, kb * GEMM_BK, m0);
+                    tma_load_2d_2sm(&tmap_b, lfull, smem_b + stage * Cfg::B_BYTES, kb * GEMM_BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
