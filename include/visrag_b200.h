@@ -146,9 +146,8 @@ int vr_attention(const vr_attn_params* p, void* stream);
  * while the exps of the current one run); causal long sequences the two-tile kernel of attention2.cuh; everything else
  * the single-tile kernel.
  * test / benchmark hook (process-wide): 0 = default dispatch, 1 = always the one-tile-per-CTA kernel, 2 = attention2 wherever
- * attention4 is the default,
- * 3 = 64-key-block kernel with Q and P in tensor memory, 5 = two-tile kernel with Q in tensor memory as well
- * (both measured slower than the default; kept as tested alternatives) */
+ * attention4 is the default, 5 = two-tile kernel with Q in tensor memory as well (measured slower than the default; kept
+ * as a tested alternative) */
 void vr_attention_force_v1(int32_t variant);
 
 

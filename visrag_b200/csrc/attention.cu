@@ -2,7 +2,6 @@
 #include "common.h"
 #include "attention.cuh"
 #include "attention2.cuh"
-#include "attention3.cuh"
 #include "attention4.cuh"
 
 namespace vr {
@@ -52,24 +51,7 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
         }
     }
     if constexpr (V2) {
-        if (g_variant == 3) {
-            // experimental: 64-key blocks, double-buffered S / P in shared memory (attention3.cuh)
-            using Cfg3 = Att3Cfg<HS>;
-            AttMaps3 m3;
-            memset(&m3, 0, sizeof(m3));
-            if (int rc = make_tmap_2d(&m3.k64, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 64, 128, true)) return rc;
-            if (int rc = make_tmap_2d(&m3.v64, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 64, 128, true)) return rc;
-            if (Cfg::HAS16) {
-                if (int rc = make_tmap_2d(&m3.k16, p.k, p.kv_rows, kcols, p.ldk, ATT3_BN, 16, 32, true)) return rc;
-                if (int rc = make_tmap_2d(&m3.v16, p.v, p.kv_rows, vcols, p.ldv, ATT3_BN, 16, 32, true)) return rc;
-            }
-            auto kern = attention3_tcgen05_kernel<HS, CAUSAL>;
-            static unsigned long long attr_set3 = 0;
-            if (first_use_on_device(&attr_set3))
-                VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES));
-            dim3 grid((p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, p.batch);
-            kern<<<grid, ATT3_THREADS, Cfg3::SMEM_BYTES, stream>>>(m3, a);
-        } else {
+        {
             // sequences longer than one query tile: two 128-query tiles per CTA in ping-pong, P and O in tensor memory
             using Cfg2 = Att2Cfg<HS>;
             // variant 5: Q in tensor memory as well (TS-MMA for Q.K^T). Measured SLOWER than Q in shared memory (1.20 vs
@@ -99,7 +81,7 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
 }  // namespace vr
 
 // test hook: 0 = default kernels, 1 = force the single-tile kernel for every shape, 2 = round-1 two-tile kernel (attention2)
-// where the persistent attention4 kernel is the default, 3 = experimental attention3 kernel,
+// where the persistent attention4 kernel is the default,
 // 5 = two-tile kernel with Q in tensor memory too (slower; kept as a measured alternative)
 extern "C" void vr_attention_force_v1(int32_t variant) { vr::g_variant = variant; }
 
