@@ -74,8 +74,6 @@ int vr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t ab_d
  *   block_n = 2    CTA-pair kernel (tcgen05 cta_group::2, one 256x256 tile per pair of SMs, each CTA stages half of B);
  *                  LINEAR epilogues with N % 192 == 0, N % 256 != 0 and K <= 2304 (proj: N = K = 1152) use 256x192 tiles
  *   block_n = 4    CTA-pair kernel with 256x192 tiles forced (LINEAR epilogues only)
- *   block_n = 5    CTA-pair kernel with the weight as the 256-row M operand and 128 tokens as N (feature-major accumulator,
- *                  LINEAR epilogues only): what vr_gemm picks for LINEAR epilogues when M <= 128 and N >= 256
  *   block_n = 256 / 128 / 64   single-CTA kernel, token-major accumulator, 128 tokens x block_n features per tile
  *   block_n = 3    single-CTA kernel, feature-major accumulator (the weight tile is the MMA's M operand), LINEAR
  *                  epilogues only; its epilogue needs no shared-memory transpose */

@@ -90,7 +90,7 @@ def case_epilogues(bn):
         x = resid[:M3].clone()
         got = ops.gemm(a4, w, resid=x, out=x, out_dtype=torch.float32, block_n=bn)
         ok &= report(f"resid in-place f32 M={M3}", got, ref_linear(a4, w, resid=resid[:M3]), 2e-3)
-    if bn in (3, 4, 5):
+    if bn in (3, 4):
         return ok  # the feature-major kernel and the 192-wide pair tiles implement LINEAR epilogues only
     # RoPE epilogue
     T, H = 300, 2304

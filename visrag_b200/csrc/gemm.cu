@@ -27,23 +27,17 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, c
     return 0;
 }
 
-template <int MODE, bool OUT_F32, bool GELU, int BN = 256, bool SWAP = false>
+template <int MODE, bool OUT_F32, bool GELU, int BN = 256>
 static int launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t stream) {
     using Cfg = Gemm2CfgT<BN>;
     CUtensorMap ta, tb;
-    if (SWAP) {  // the weight takes the 128-row boxes of the MMA's M side, the activations the BN/2-row boxes of its N side
-        if (int rc = make_tmap_2d(&ta, B, g.N, g.K, ldb, GEMM_BM, GEMM_BK, 128, true)) return rc;
-        if (int rc = make_tmap_2d(&tb, A, g.M, g.K, lda, BN / 2, GEMM_BK, 128, true)) return rc;
-    } else {
-        if (int rc = make_tmap_2d(&ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, true)) return rc;
-        if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, BN / 2, GEMM_BK, 128, true)) return rc;
-    }
-    auto kern = gemm2_tcgen05_kernel<MODE, OUT_F32, GELU, BN, SWAP>;
+    if (int rc = make_tmap_2d(&ta, A, g.M, g.K, lda, GEMM_BM, GEMM_BK, 128, true)) return rc;
+    if (int rc = make_tmap_2d(&tb, B, g.N, g.K, ldb, BN / 2, GEMM_BK, 128, true)) return rc;
+    auto kern = gemm2_tcgen05_kernel<MODE, OUT_F32, GELU, BN>;
     static unsigned long long attr_set = 0;
     if (first_use_on_device(&attr_set))
         VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    const int tiles = SWAP ? ((g.N + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((g.M + Cfg::BN - 1) / Cfg::BN)
-                           : ((g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((g.N + Cfg::BN - 1) / Cfg::BN);
+    const int tiles = ((g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((g.N + Cfg::BN - 1) / Cfg::BN);
     // A persistent kernel must not launch more clusters than can be co-resident: GPCs with an odd number of usable SMs
     // cannot pair all of them, and a cluster that has to wait for a free pair would run its whole tile list after the
     // others finished (measured: 74 clusters requested -> about half the throughput). Ask the driver.
@@ -112,19 +106,6 @@ static int dispatch_mode2(const void* A, int64_t lda, const void* B, int64_t ldb
             set_error("vr_gemm: unknown epilogue mode %d", e.mode);
             return 2;
     }
-}
-
-// CTA pair with the weight as the M operand (block_n == 5): LINEAR epilogues only; the small-batch form
-static int dispatch_pair_swapped(const void* A, int64_t lda, const void* B, int64_t ldb, const GemmArgs& g, cudaStream_t s) {
-    const vr_gemm_epilogue& e = g.epi;
-    VR_REQUIRE(e.mode == VR_EPI_LINEAR, "vr_gemm: block_n=5 (CTA pair, feature-major accumulator) supports LINEAR epilogues only");
-    if (e.out_dtype == VR_F32) {
-        VR_REQUIRE(!e.act_gelu, "vr_gemm: GELU epilogue writes bf16 only");
-        return launch_gemm2<VR_EPI_LINEAR, true, false, 128, true>(A, lda, B, ldb, g, s);
-    }
-    VR_REQUIRE(e.out_dtype == VR_BF16, "vr_gemm: out_dtype must be VR_BF16 or VR_F32");
-    if (e.act_gelu) return launch_gemm2<VR_EPI_LINEAR, false, true, 128, true>(A, lda, B, ldb, g, s);
-    return launch_gemm2<VR_EPI_LINEAR, false, false, 128, true>(A, lda, B, ldb, g, s);
 }
 
 // feature-major accumulator kernels (block_n == 3): LINEAR epilogues only
@@ -199,9 +180,6 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
         // M <= 128 (a few queries): one row tile, the kernel only streams the weight - 64-wide feature tiles spread that
         // stream over 4x as many SMs as 256-wide ones (o_proj 2304x2304: 36 CTAs instead of 9)
         bn = (M > 128 && N >= 256) ? 2 : (M <= 128 ? 64 : (N >= 256 ? 256 : 128));
-        // ... and for LINEAR epilogues the pair kernel with the weight on the M side: each SM then loads two weight bytes per
-        // activation byte instead of one per two (LM o / down with one query: 19 + 31 us -> measured below)
-        if (M <= 128 && N >= 256 && epi->mode == VR_EPI_LINEAR && (epi->ldo & 1) == 0) bn = 5;
     }
     if (bn == 2 || bn == 4) {
         const bool force192 = bn == 4;
@@ -213,11 +191,10 @@ extern "C" int vr_gemm_tuned(const void* A, int64_t lda, const void* B, int64_t 
         return dispatch_mode2(A, lda, B, ldb, g, s, force192, narrow_ok != 0);
     }
     if (bn == 3) return dispatch_swapped(A, lda, B, ldb, g, s);
-    if (bn == 5) return dispatch_pair_swapped(A, lda, B, ldb, g, s);
     if (bn == 256) return dispatch_mode<256>(A, lda, B, ldb, g, s);
     if (bn == 128) return dispatch_mode<128>(A, lda, B, ldb, g, s);
     if (bn == 64) return dispatch_mode<64>(A, lda, B, ldb, g, s);
-    set_error("vr_gemm: block_n must be 0 (auto), 64, 128, 256, 2 (CTA-pair kernel), 4 (CTA pair, 192-wide tiles), 5 (CTA pair, weight on the M side) or 3 (feature-major accumulator)");
+    set_error("vr_gemm: block_n must be 0 (auto), 64, 128, 256, 2 (CTA-pair kernel), 4 (CTA pair, 192-wide tiles) or 3 (feature-major accumulator)");
     return 2;
 }
 

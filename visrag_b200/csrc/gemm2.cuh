@@ -27,18 +27,12 @@ struct Gemm2CfgT {
 };
 using Gemm2Cfg = Gemm2CfgT<256>;
 
-// SWAP (LINEAR only, BN_ = 128): the WEIGHT is the 256-row M operand (tmap_a, 128 feature rows per CTA) and the tokens are
-// the N operand (tmap_b, BN_ tokens per tile, each CTA stages half of them); the accumulator is feature-major and leaves
-// through epi_linear_t. This is the small-batch form: with M <= 128 tokens a tile's traffic is 2/3 weight, 1/3
-// activations (token-major 128 x 64 tiles: 1/3 weight, 2/3 activation rows re-read by every tile), so the SMs that
-// stream a 2304-row weight spend their L2 bandwidth on the weight.
-template <int MODE, bool OUT_F32, bool GELU, int BN_ = 256, bool SWAP = false>
+template <int MODE, bool OUT_F32, bool GELU, int BN_ = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const GemmArgs g) {
     using Cfg = Gemm2CfgT<BN_>;
-    static_assert(BN_ == 256 || ((BN_ == 192 || BN_ == 128) && MODE == VR_EPI_LINEAR), "narrow tiles: LINEAR epilogues only");
-    static_assert(!SWAP || MODE == VR_EPI_LINEAR, "feature-major accumulators are implemented for LINEAR epilogues");
+    static_assert(BN_ == 256 || (BN_ == 192 && MODE == VR_EPI_LINEAR), "192-wide tiles: LINEAR epilogues only");
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BN = Cfg::BN;
 
@@ -61,8 +55,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
 
-    const int tiles_m = ((SWAP ? g.N : g.M) + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-    const int tiles_n = ((SWAP ? g.M : g.N) + BN - 1) / BN;
+    const int tiles_m = (g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int tiles_n = (g.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
 
@@ -147,7 +141,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     } else if (warp == 3) {
         // ------------------------------------------------------------ residual prefetcher (both CTAs, own 128 rows);
         // see gemm.cuh: pulls tile i's fp32 residual rows into L2 while tile i's main loop runs
-        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.prefetch_resid && !SWAP) {
+        if (MODE == VR_EPI_LINEAR && OUT_F32 && g.prefetch_resid) {
             int it = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 uint32_t started;
@@ -180,7 +174,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int row0 = m0 + quarter * 32;
             const uint32_t ltempty = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == VR_EPI_LINEAR && !SWAP) bias4 = epi_bias_prefetch(g, lane, n0 + half * COLS_PER_WARP, COLS_PER_WARP);
+            if (MODE == VR_EPI_LINEAR) bias4 = epi_bias_prefetch(g, lane, n0 + half * COLS_PER_WARP, COLS_PER_WARP);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
@@ -198,8 +192,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (SWAP) epi_linear_t<OUT_F32, GELU>(g, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v);  // rows = features
-                    else epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v, bias4, c);
+                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v, bias4, c);
                 }
             } else {
 #pragma unroll 1
