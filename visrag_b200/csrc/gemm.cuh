@@ -188,6 +188,24 @@ __device__ __forceinline__ void stage_load_wide_f32(uint8_t* st, int lane, const
         *reinterpret_cast<uint4*>(st + wide_off(r, u)) = q[i];
     }
 }
+// The two halves of stage_load_wide_f32 as separate steps: the pair kernel issues a chunk's residual loads one chunk (for
+// the first chunk: one tile) ahead, so their latency is off the epilogue's critical path (epi_linear<.., PRE = true>).
+__device__ __forceinline__ void resid_issue(uint4 (&q)[8], int lane, const float* gbase, long long ld, int row0, int rows_valid,
+                                            int col0, int cols_valid) {
+    const int u = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        q[i] = make_uint4(0, 0, 0, 0);
+        if (r < rows_valid && u * 4 < cols_valid)
+            q[i] = *reinterpret_cast<const uint4*>(gbase + static_cast<long long>(row0 + r) * ld + col0 + u * 4);
+    }
+}
+__device__ __forceinline__ void resid_to_stage(uint8_t* st, int lane, const uint4 (&q)[8]) {
+    const int u = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(st + wide_off(i * 4 + (lane >> 3), u)) = q[i];
+}
 __device__ __forceinline__ void stage_put_half(uint8_t* st, int lane, const uint32_t (&w)[16]) {
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -219,9 +237,11 @@ __device__ __forceinline__ float4 epi_bias_prefetch(const GemmArgs& g, int lane,
     return b;
 }
 
-template <bool OUT_F32, bool GELU>
+// PRE: the residual of this chunk was loaded into `q` beforehand (resid_issue); after it has been consumed, the loads of the
+// chunk at `next_col0` (< 0: none) are issued into the same registers, ahead of this chunk's output stores.
+template <bool OUT_F32, bool GELU, bool PRE = false>
 __device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int lane, int row0, int col0, float (&x)[32],
-                                           const float4& bias4, int chunk) {
+                                           const float4& bias4, int chunk, uint4 (*q)[8] = nullptr, int next_col0 = -1) {
     const vr_gemm_epilogue& e = g.epi;
     const int rows_valid = g.M - row0;          // may exceed 32
     const int cols_valid = g.N - col0;          // may exceed 32; N % 8 == 0
@@ -255,13 +275,15 @@ __device__ __forceinline__ void epi_linear(const GemmArgs& g, uint8_t* st, int l
         }
     }
     if (e.resid) {
-        stage_load_wide_f32(st, lane, e.resid, e.ldo, row0, rows_valid, col0, cols_valid);
+        if (PRE) resid_to_stage(st, lane, *q);
+        else stage_load_wide_f32(st, lane, e.resid, e.ldo, row0, rows_valid, col0, cols_valid);
         __syncwarp();
         uint32_t w[32];
         stage_get_wide(st, lane, w);
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(w[j]);
         __syncwarp();
+        if (PRE && next_col0 >= 0) resid_issue(*q, lane, e.resid, e.ldo, row0, rows_valid, next_col0, g.N - next_col0);
     }
     if (OUT_F32) {
         uint32_t w[32];

@@ -175,6 +175,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const uint32_t ltempty = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (MODE == VR_EPI_LINEAR) bias4 = epi_bias_prefetch(g, lane, n0 + half * COLS_PER_WARP, COLS_PER_WARP);
+            // fp32 residual: the first chunk's loads fly while this tile's main loop finishes, every later chunk's while the
+            // chunk before it is stored (ncu on proj, K = 1152: the epilogue warps sat on these loads, long_scoreboard 3.6,
+            // tensor pipe 55 %)
+            constexpr bool PRE = MODE == VR_EPI_LINEAR && OUT_F32;
+            const bool pre = PRE && g.epi.resid != nullptr;
+            uint4 rq[8];
+            if (pre) {
+                const int c0 = n0 + half * COLS_PER_WARP;
+                resid_issue(rq, lane, g.epi.resid, g.epi.ldo, row0, g.M - row0, c0, g.N - c0);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
@@ -192,7 +202,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epi_linear<OUT_F32, GELU>(g, st, lane, row0, n0 + half * COLS_PER_WARP + c * 32, v, bias4, c);
+                    const int col = n0 + half * COLS_PER_WARP + c * 32;
+                    if (pre)
+                        epi_linear<OUT_F32, GELU, PRE>(g, st, lane, row0, col, v, bias4, c, &rq,
+                                                       c + 1 < COLS_PER_WARP / 32 ? col + 32 : -1);
+                    else
+                        epi_linear<OUT_F32, GELU>(g, st, lane, row0, col, v, bias4, c);
                 }
             } else {
 #pragma unroll 1
