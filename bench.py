@@ -517,7 +517,7 @@ def cpu_port_baseline(cfg, sd_cpu, tok, pages, page_px):
     except OSError:
         pass
     return {"value": round(done / dt, 4), "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "cpu_model": cpu_model, "kind": "port",
-            "sample": f"{done} pages {page_px}x{page_px}, full model, fp32, oracle/restated.py", "seconds": round(dt, 1),
+            "sample": f"{done} pages {page_px}x{page_px}, {'full' if cfg.layers == 40 else 'reduced'} model, fp32, oracle/restated.py", "seconds": round(dt, 1),
             "retrieval": {"queries_per_s": round(1000 / rt, 1), "sample": "1000 queries x 10000 pages x 2304, fp32 matmul + top-10 (oracle.score_topk)",
                           "seconds": round(rt, 2)}}
 

@@ -20,8 +20,8 @@ from visrag_b200.weights import random_state_dict_device  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--pages", default="128,256")
-    ap.add_argument("--vit-tokens", default="16384,32768,65536,131072")
+    ap.add_argument("--pages", default="112,120,128,144,150,256")
+    ap.add_argument("--vit-tokens", default="65536,131072,163840")
     ap.add_argument("--steps", type=int, default=4)
     a = ap.parse_args()
     from PIL import Image

@@ -385,6 +385,8 @@ class VisRAGEngine:
         ent = self._graphs.get(sig)
         if ent is None:
             seen = self._graph_seen.get(sig, 0)
+            if len(self._graph_seen) > 4096:  # a stream of never-repeating shapes must not grow this without bound
+                self._graph_seen.clear()
             self._graph_seen[sig] = seen + 1
             if seen == 0:
                 self.graph_stats["eager"] += 1
