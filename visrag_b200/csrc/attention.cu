@@ -80,6 +80,12 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
 
 }  // namespace vr
 
+#if VR_A_TRACE
+extern "C" int vr_attention_trace_read(long long* out) {
+    return cudaMemcpyFromSymbol(out, vr::g_att_trace, sizeof(vr::g_att_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 // test hook: 0 = default kernels, 1 = force the single-tile kernel for every shape, 2 = round-1 two-tile kernel (attention2)
 // where the persistent attention4 kernel is the default,
 // 5 = two-tile kernel with Q in tensor memory too (slower; kept as a measured alternative)

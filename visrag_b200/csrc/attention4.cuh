@@ -36,6 +36,18 @@
 
 namespace vr {
 
+#ifndef VR_A_TRACE
+#define VR_A_TRACE 0
+#endif
+#if VR_A_TRACE
+// Debug build only (tools/trace_attention.py): clock64 stamps of CTA 0's softmax warps 0 (tile A) and 4 (tile B), and of
+// the MMA issuer, for the first 96 key blocks.
+__device__ long long g_att_trace[3][96][8];
+#define VR_TR(x, blk, slot) do { if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && (blk) < 96) g_att_trace[x][blk][slot] = clock64(); } while (0)
+#else
+#define VR_TR(x, blk, slot) do { } while (0)
+#endif
+
 constexpr int ATT4_THREADS = 384;
 
 template <int HS>
@@ -234,6 +246,9 @@ attention4_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a,
                                 const int j = jq[x];
                                 const bool release_k = jq[x ^ 1] > j;  // the other tile already used (or never uses) this K stage
                                 if (elect_one()) {
+#if VR_A_TRACE
+                                    if (blockIdx.x == 0 && cs[x] < 96) g_att_trace[2][cs[x]][x * 2] = clock64();
+#endif
                                     issue_qk(qbase + (qb * 2 + x) * TILE16, kbase + st * TILE16, tmem_base + Cfg::T_S + x * 128);
                                     umma_commit(&s_full[x]);
                                     if (release_k) umma_commit(&k_empty[st]);
@@ -255,6 +270,9 @@ attention4_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a,
                                 const int j = jp[x];
                                 const bool release_v = jp[x ^ 1] > j;
                                 if (elect_one()) {
+#if VR_A_TRACE
+                                    if (blockIdx.x == 0 && cp[x] < 96) g_att_trace[2][cp[x]][x * 2 + 1] = clock64();
+#endif
                                     issue_pv(vbase + st * TILE16, tmem_base + Cfg::T_O + x * HS, j == 0);
                                     umma_commit(&pv_done[x]);
                                     if (release_v) umma_commit(&v_empty[st]);
@@ -303,14 +321,17 @@ attention4_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a,
                 for (int kt = 0; kt < nkt; ++kt, ++n_mine) {
                     const int limit = it.len_k - kt * ATT_BN;
                     const bool full = limit >= ATT_BN;
+                    VR_TR(x, n_mine, 0);
                     mbar_wait(&s_full[x], n_mine & 1);
                     tc_fence_after();
+                    VR_TR(x, n_mine, 1);
                     uint32_t sv[4][32];
                     tmem_ld_32x32(tmem_s, sv[0]);
                     tmem_ld_32x32(tmem_s + 32, sv[1]);
                     tmem_ld_32x32(tmem_s + 64, sv[2]);
                     tmem_ld_32x32(tmem_s + 96, sv[3]);
                     tmem_ld_wait();
+                    VR_TR(x, n_mine, 2);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_free[x]);  // QK of the next key block may overwrite S_x now
@@ -383,6 +404,7 @@ attention4_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a,
                     const float neg_ms = -m_ref * sl2;
                     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                     uint32_t pk[4][16];
+                    VR_TR(x, n_mine, 3);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float p[32];
@@ -410,14 +432,17 @@ attention4_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a,
 #pragma unroll
                         for (int j = 0; j < 16; ++j) pk[c][j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
                     }
+                    VR_TR(x, n_mine, 4);
                     if (!waited && pred_tile >= 0) {
                         mbar_wait(&pv_done[pred_tile], pred_idx & 1);
                         tc_fence_after();
                     }
+                    VR_TR(x, n_mine, 5);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tmem_st_32x16(tmem_p + c * 16, pk[c]);
                     if (!ONES) l_run += (l0 + l1) + (l2 + l3);
                     tmem_st_wait();
+                    VR_TR(x, n_mine, 6);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&p_full[x]);
