@@ -33,6 +33,7 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
     a.ldo = p.ldo;
     a.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
     a.ldq = p.ldq;
+    a.tma_out = 0;
     if constexpr (V2 && !CAUSAL) {
         if (g_variant == 0) {
             // default for long non-causal sequences (the ViT): persistent decoupled kernel, attention4.cuh
@@ -40,6 +41,11 @@ static int launch_attention(const vr_attn_params& p, cudaStream_t stream) {
             const bool ones = (p.flags & VR_ATTN_V_ONES_COLUMN) != 0;
             const int nqp = (p.max_q + 2 * ATT_BM - 1) / (2 * ATT_BM);
             const long long items = static_cast<long long>(nqp) * p.heads * p.batch;
+            // output tile store: 128 rows x head_dim columns per (tile, head), plain row-major box (no swizzle)
+            if (p.cu_q && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.head_dim % 8 == 0) {
+                if (int rc = make_tmap_2d(&maps.o, p.out, p.q_rows, p.ldo, p.ldo, ATT_BM, p.head_dim, 0, true)) return rc;
+                a.tma_out = 1;
+            }
             auto kern = ones ? attention4_tcgen05_kernel<HS, true> : attention4_tcgen05_kernel<HS, false>;
             static unsigned long long attr_set4[2] = {0, 0};
             if (first_use_on_device(&attr_set4[ones]))

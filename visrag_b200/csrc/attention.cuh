@@ -54,10 +54,12 @@ struct AttArgs {
     long long ldo;
     const __nv_bfloat16* q;  // query matrix base (kernels that stage Q themselves instead of through TMA)
     long long ldq;
+    int tma_out;             // attention4: maps.o is valid, full 128-row tiles leave through a bulk tensor store
 };
 
 struct AttMaps {
     CUtensorMap q64, q16, k64, k16, v64, v16;
+    CUtensorMap o;  // output [rows, ldo] with a 128-row x head_dim box (attention4's bulk-store epilogue); unused elsewhere
 };
 
 template <int HS, bool CAUSAL>
