@@ -329,19 +329,31 @@ attention4_tcgen05_kernel(const __grid_constant__ AttMaps maps, const AttArgs a,
                     uint32_t sv[4][32];
                     tmem_ld_32x32(tmem_s, sv[0]);
                     tmem_ld_32x32(tmem_s + 32, sv[1]);
-                    tmem_ld_32x32(tmem_s + 64, sv[2]);
-                    tmem_ld_32x32(tmem_s + 96, sv[3]);
                     tmem_ld_wait();
-                    VR_TR(x, n_mine, 2);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_free[x]);  // QK of the next key block may overwrite S_x now
+                    tmem_ld_32x32(tmem_s + 64, sv[2]);  // second half in flight while the first half's maximum is taken
+                    tmem_ld_32x32(tmem_s + 96, sv[3]);
                     float m_tile;
                     {
                         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
                         if (full) {
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    m0 = max3(m0, __uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]));
+                                    m1 = max3(m1, __uint_as_float(sv[c][j + 2]), __uint_as_float(sv[c][j + 3]));
+                                    m2 = max3(m2, __uint_as_float(sv[c][j + 4]), __uint_as_float(sv[c][j + 5]));
+                                    m3 = max3(m3, __uint_as_float(sv[c][j + 6]), __uint_as_float(sv[c][j + 7]));
+                                }
+                        }
+                        tmem_ld_wait();
+                        VR_TR(x, n_mine, 2);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s_free[x]);  // QK of the next key block may overwrite S_x now
+                        if (full) {
+#pragma unroll
+                            for (int c = 2; c < 4; ++c)
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) {
                                     m0 = max3(m0, __uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]));
