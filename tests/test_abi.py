@@ -40,3 +40,20 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no fallback"):
         L.lib()
+
+
+def test_score_plan_is_host_logic_and_bounded():
+    """vr_score_ranges (the candidate-buffer sizing the caller needs before vr_score_filter) is pure host arithmetic: it must
+    answer without a GPU (148 SMs assumed) and stay within the rescoring kernel's list limit for any problem size."""
+    import ctypes as C
+
+    from visrag_b200 import _lib as L
+
+    lib = L.lib()
+    lib.vr_score_ranges.restype = C.c_int32
+    lib.vr_score_ranges.argtypes = [C.c_int32, C.c_int64]
+    assert lib.vr_score_list_len() == 16
+    for nq, nd in ((1, 256), (1, 1_000_000), (5, 1_000_000), (129, 4097), (1000, 10_000), (10_000, 125_000), (100_000, 10_000_000)):
+        r = lib.vr_score_ranges(nq, nd)
+        assert 1 <= r <= 33, (nq, nd, r)
+    assert lib.vr_score_ranges(10_000, 125_000) <= 8          # few lists per query where the rescoring cost matters

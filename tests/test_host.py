@@ -83,3 +83,39 @@ def test_text_only_and_errors():
         host.prepare_batch([""], [Image.new("RGB", (224, 224))], tok, CFG, 40)  # span cut by truncation
     with pytest.raises(NotImplementedError):
         host.prepare_batch([["chat"]], [None], tok, CFG)
+
+
+def test_graph_plan_buckets_text_batches_and_leaves_pages_alone():
+    """Host side of the CUDA-graph path (encoder._graph_plan): text-only batches are padded to 16-token buckets with ONE extra
+    dummy sequence (token id 0, positions 0..pad-1) so that different queries share a captured graph; batches with pages keep
+    their exact arrays; oversized batches are not graphed."""
+    from types import SimpleNamespace
+
+    import numpy as np
+
+    from visrag_b200.config import VisRAGConfig
+    from visrag_b200.encoder import GRAPH_MAX_LM_TOKENS, GRAPH_TEXT_BUCKET, VisRAGEngine
+    from visrag_b200.host import prepare_batch
+    from visrag_b200.synth import synth_pages
+    from visrag_b200.tokenizer_stub import StubTokenizer
+
+    cfg = VisRAGConfig.tiny()
+    tok = StubTokenizer(cfg.vocab)
+    eng = SimpleNamespace(cuda_graphs=True, cfg=cfg)
+    for texts in (["a"], ["hello world this is", "x"], ["q" * 31], ["q" * 14, "r" * 15, "s" * 16]):
+        pb = prepare_batch(texts, [None] * len(texts), tok, cfg, 2048)
+        src, pos, cu, max_len, n_out = VisRAGEngine._graph_plan(eng, pb)
+        T = int(pb.cu_seqlens[-1])
+        assert n_out == len(texts) and len(cu) == len(texts) + 2
+        assert len(src) == len(pos) == cu[-1] and cu[-1] % GRAPH_TEXT_BUCKET == 0 and cu[-1] > T      # at least one pad token
+        assert np.array_equal(src[:T], pb.token_src) and np.array_equal(pos[:T], pb.positions) and np.array_equal(cu[:-1], pb.cu_seqlens)
+        pad = cu[-1] - T
+        assert (src[T:] == -1).all() and np.array_equal(pos[T:], np.arange(pad))                      # token id 0, its own positions
+        assert max_len % GRAPH_TEXT_BUCKET == 0 and max_len >= max(int(pb.seq_lens.max()), pad)
+    pages = synth_pages([(448, 448), (300, 500)], 3)
+    pb = prepare_batch(["", ""], pages, tok, cfg, 2048)
+    src, pos, cu, max_len, n_out = VisRAGEngine._graph_plan(eng, pb)
+    assert src is pb.token_src and cu is pb.cu_seqlens and max_len == int(pb.seq_lens.max()) and n_out == 2
+    big = prepare_batch(["w" * 600] * 8, [None] * 8, tok, cfg, 2048)                                # > GRAPH_MAX_LM_TOKENS tokens
+    assert int(big.cu_seqlens[-1]) > GRAPH_MAX_LM_TOKENS and VisRAGEngine._graph_plan(eng, big) is None
+    assert VisRAGEngine._graph_plan(SimpleNamespace(cuda_graphs=False, cfg=cfg), pb) is None
