@@ -391,14 +391,25 @@ class VisRAGEngine:
             if seen == 0:
                 self.graph_stats["eager"] += 1
                 return self.encode_device(groups, group_row0, n_slices, src, pos, cu, max_len, pooling, normalize)
+            if seen < 0:  # an earlier capture of this shape failed: stay on eager launches
+                self.graph_stats["eager"] += 1
+                return self.encode_device(groups, group_row0, n_slices, src, pos, cu, max_len, pooling, normalize)
             ent = _GraphEntry()
             ent.groups = {k: v.clone() for k, v in groups.items()}
             ent.src, ent.pos, ent.cu = src.clone(), pos.clone(), cu.clone()
             launches0 = L.LAUNCHES
             torch.cuda.synchronize(self.device)
             ent.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ent.graph):
-                ent.reps = self.encode_device(ent.groups, group_row0, n_slices, ent.src, ent.pos, ent.cu, max_len, pooling, normalize)
+            try:
+                with torch.cuda.graph(ent.graph):
+                    ent.reps = self.encode_device(ent.groups, group_row0, n_slices, ent.src, ent.pos, ent.cu, max_len, pooling, normalize)
+            except Exception as exc:  # the capture is an optimisation of the launch path only: same kernels, eager launches
+                import warnings
+
+                warnings.warn(f"visrag_b200: CUDA-graph capture failed for this batch shape ({exc!r}); using eager launches")
+                self._graph_seen[sig] = -(1 << 30)
+                self.graph_stats["eager"] += 1
+                return self.encode_device(groups, group_row0, n_slices, src, pos, cu, max_len, pooling, normalize)
             ent.launches = L.LAUNCHES - launches0
             self._graphs[sig] = ent
             self.graph_stats["captured"] += 1
