@@ -158,7 +158,9 @@ void vr_attention_force_v1(int32_t variant);
 /* uint8 HWC slices -> normalised bf16 patch matrix (ToTensor + Normalize(0.5,0.5) + the unfold of the
  * 14x14/stride-14 patch conv): modeling_minicpmv.py:84-92 + timm/layers/patch_embed.py:87.
  * pixels: [n_slices, h, w, 3] uint8 (h, w multiples of `patch`); out: [n_slices*(h/patch)*(w/patch), ldo] bf16,
- * column c*patch*patch + ky*patch + kx (the Conv2d weight's flattening); columns [3*patch^2, ldo) are zeroed. */
+ * column c*patch*patch + ky*patch + kx (the Conv2d weight's flattening); columns [3*patch^2, ldo) are zeroed.
+ * bf16(fma(u, 2/255, -1)) - bit-identical to bf16((u/255 - 0.5)/0.5) for all 256 byte values. patch <= 85; a strip of `patch`
+ * pixel rows must fit 200 KB of shared memory (w up to ~4800 for patch 14). */
 int vr_im2col_norm(const uint8_t* pixels, int32_t n_slices, int32_t h, int32_t w, int32_t patch, void* out, int64_t ldo,
                    void* stream);
 
@@ -180,7 +182,9 @@ int vr_build_lm_input(const int32_t* src, int32_t tokens, int32_t dim, const voi
 
 /* Final RMSNorm + pooling + L2 normalise (modeling_minicpm.py:1280; dense_retrieval_model.py:170-223):
  * per packed sequence b (rows cu[b]..cu[b+1]) of h [tokens, dim] fp32 -> reps [batch, dim] fp32.
- * pooling: 0 wmean (w_t = t+1), 1 mean, 2 lasttoken, 3 cls. normalise: x / max(||x||, 1e-12). */
+ * pooling: 0 wmean (w_t = t+1), 1 mean, 2 lasttoken, 3 cls. normalise: x / max(||x||, 1e-12).
+ * One thread-block cluster of 8 (or 4) CTAs per sequence, every row read once; h, gamma and reps 16-byte aligned; any
+ * sequence length (no per-length shared memory), dim <= 4096. */
 int vr_pool_norm(const float* h, int64_t ldh, const float* gamma, float eps, const int32_t* cu, int32_t batch, int32_t dim,
                  int32_t pooling, int32_t normalize, float* reps, void* stream);
 
@@ -189,13 +193,18 @@ int vr_pool_norm(const float* h, int64_t ldh, const float* gamma, float eps, con
  * Similarity + top-k: replaces `torch.matmul(Q, D^T)` + `torch.topk` of
  * retriever/dense_retriever.py:25-30 (fp32 scores) and the Python merge loop `:88-92`.
  * The [nq, nd] score matrix is never materialised:
- *   vr_score_filter  : tcgen05 fp16 GEMM with a fused per-row running top-16 (per query block x doc range);
- *   vr_score_rescore : exact fp32 rescoring of the survivors + top-k by (score desc, id asc) + a proof that
- *                      nothing dropped could belong to the top-k (flags[q] = 1 when the proof fails; the caller
- *                      then reruns that query through vr_score_exact + vr_topk_rows).
+ *   vr_score_filter  : tcgen05 fp16 GEMM on CTA pairs (256 queries x 256 docs per MMA tile) with a fused per-row running
+ *                      top-16 per (query, doc range); writes `lists = 2*ranges` sorted 16-entry candidate lists per query into
+ *                      cand_scores / cand_ids [nq, lists*16] (unused lists: score -inf, id -1; the first score of the LAST
+ *                      list slot is scratch - the query's running threshold - and carries id -1);
+ *   vr_score_rescore : keeps the max(32, 2k) best candidates by approximate score, rescoring them exactly in fp32, top-k by
+ *                      (score desc, id asc), and a proof that nothing dropped (by a list or by the pruning) could belong to
+ *                      the top-k (flags[q] = 1 when the proof fails; the caller then reruns that query through
+ *                      vr_score_exact + vr_topk_rows).
  * Results are therefore exactly the fp32 top-k. Doc ids returned are `local index + id_offset`.
  * ---------------------------------------------------------------------------------- */
-int vr_score_ranges(int32_t nq, int64_t nd);   /* doc ranges the filter uses: cand buffers are [nq, ranges*2*16] */
+int vr_score_ranges(int32_t nq, int64_t nd);   /* sizes the candidate buffers: [nq, ranges*2*16]; host arithmetic only (needs no
+                                                * GPU); pass the value on to vr_score_filter / vr_score_rescore unchanged */
 int vr_score_list_len(void);                   /* 16 */
 int vr_f32_to_f16_rows(const float* src, int64_t rows, int32_t dim, void* dst_f16, float* norms, float* max_norm,
                        void* stream);          /* norms / max_norm optional; *max_norm must be pre-zeroed */
