@@ -206,6 +206,10 @@ int vr_pool_norm(const float* h, int64_t ldh, const float* gamma, float eps, con
 int vr_score_ranges(int32_t nq, int64_t nd);   /* sizes the candidate buffers: [nq, ranges*2*16]; host arithmetic only (needs no
                                                 * GPU); pass the value on to vr_score_filter / vr_score_rescore unchanged */
 int vr_score_list_len(void);                   /* 16 */
+/* The filter's work decomposition for (nq, nd), host arithmetic only: out6 = {doc tiles of 256, doc ranges R, 256-query blocks,
+ * work items = R * blocks (item i = range i / blocks of query block i % blocks, tiles [T*r/R, T*(r+1)/R)), CTA pairs launched,
+ * candidate lists per query (= 2 * vr_score_ranges)}. For tests and capacity planning. */
+int vr_score_plan(int32_t nq, int64_t nd, int32_t* out6);
 int vr_f32_to_f16_rows(const float* src, int64_t rows, int32_t dim, void* dst_f16, float* norms, float* max_norm,
                        void* stream);          /* norms / max_norm optional; *max_norm must be pre-zeroed */
 int vr_score_filter(const void* q_f16, int32_t nq, const void* d_f16, int64_t nd, int32_t dim, int32_t ranges,

@@ -86,6 +86,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vr_score_ranges.argtypes = [i32, i64]
     lib.vr_score_list_len.restype = i32
     lib.vr_score_list_len.argtypes = []
+    lib.vr_score_plan.restype = i32
+    lib.vr_score_plan.argtypes = [i32, i64, vp]
     lib.vr_f32_to_f16_rows.restype = i32
     lib.vr_f32_to_f16_rows.argtypes = [vp, i64, i32, vp, vp, vp, vp]
     lib.vr_score_filter.restype = i32

@@ -764,6 +764,12 @@ static int score_ranges_for(int nq, long long nd) { return score_plan(nq, nd).li
 using namespace vr;
 
 extern "C" int vr_score_ranges(int32_t nq, int64_t nd) { return score_ranges_for(nq, nd); }
+extern "C" int vr_score_plan(int32_t nq, int64_t nd, int32_t* out6) {
+    VR_REQUIRE(out6 && nq > 0 && nd > 0, "vr_score_plan: bad arguments");
+    const ScorePlan p = score_plan(nq, nd);
+    out6[0] = p.T; out6[1] = p.R; out6[2] = p.QB; out6[3] = p.items; out6[4] = p.pairs; out6[5] = p.lists;
+    return 0;
+}
 extern "C" int vr_score_list_len(void) { return SC_KT; }
 
 extern "C" int vr_f32_to_f16_rows(const float* src, int64_t rows, int32_t dim, void* dst_f16, float* norms, float* max_norm,
