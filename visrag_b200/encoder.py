@@ -12,10 +12,9 @@ Every kernel is a C-ABI call (visrag_b200/ops.py); torch only owns the buffers.
 from __future__ import annotations
 
 import functools
-import math
 import os
 from collections import OrderedDict
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
